@@ -1,0 +1,251 @@
+// Index builders of the self-adaptive node layer (reference: model/point_utils.py:5-165, called from
+// adapt_layer_off.forward, model/model_utils.py:103-128).  The reference runs a 64-iteration Python
+// loop with two boolean-mask host syncs per iteration plus two full sorts of [B,64,1024]; here each
+// step is one launch with no host round trip.  Only indices are produced; the differentiable
+// gathers / weights around them stay in the autograd graph of the host module.
+//
+// Floating-point forms follow the reference so that selections agree except on genuine ties:
+//   FPS:        d = (dx*dx + dy*dy) + dz*dz on explicit differences  (point_utils.py:21)
+//   the others: d = ((-2 s.d) + |s|^2) + |d|^2                        (point_utils.py:127-130)
+#include "common.cuh"
+
+namespace sug {
+
+__device__ __forceinline__ float sq3(float a, float b, float c) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c));
+}
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+  return fmaf(az, bz, fmaf(ay, by, __fmul_rn(ax, bx)));
+}
+__device__ __forceinline__ float sqdist_expanded(float dot, float nq, float np) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(-2.f, dot), nq), np);
+}
+
+// ---- farthest point sampling: one CTA per cloud ------------------------------------------------
+__global__ void __launch_bounds__(1024)
+fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int* __restrict__ start, int* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* px = sm;
+  float* py = sm + N;
+  float* pz = sm + 2 * N;
+  float* dist = sm + 3 * N;
+  __shared__ float wv[32];
+  __shared__ int wi[32];
+  __shared__ int s_far;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const float* xb = xyz + (size_t)b * 3 * N;
+  for (int i = tid; i < N; i += nt) {
+    px[i] = xb[i];
+    py[i] = xb[N + i];
+    pz[i] = xb[2 * N + i];
+    dist[i] = 1e10f;
+  }
+  if (tid == 0) s_far = start[b];
+  __syncthreads();
+  for (int r = 0; r < npoint; ++r) {
+    const int far = s_far;
+    if (tid == 0) out[(size_t)b * npoint + r] = far;
+    const float cx = px[far], cy = py[far], cz = pz[far];
+    float bv = -1.f;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < N; i += nt) {
+      float d = sq3(px[i] - cx, py[i] - cy, pz[i] - cz);
+      float cur = dist[i];
+      if (d < cur) { cur = d; dist[i] = d; }
+      if (cur > bv) { bv = cur; bi = i; }  // ascending i per thread: first maximum kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();  // everyone has read s_far
+    if ((tid & 31) == 0) { wv[tid >> 5] = bv; wi[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+      float v = tid < (nt >> 5) ? wv[tid] : -2.f;
+      int ii = tid < (nt >> 5) ? wi[tid] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, ii, o);
+        if (ov > v || (ov == v && oi < ii)) { v = ov; ii = oi; }
+      }
+      if (tid == 0) s_far = ii;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- ball query: one warp per query -------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ query, int N, int S, float r2, int nsample,
+                  int* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  if (warp >= S) return;
+  const float* xb = xyz + (size_t)b * 3 * N;
+  const float* qb = query + (size_t)b * 3 * S;
+  const float qx = qb[warp], qy = qb[S + warp], qz = qb[2 * S + warp];
+  const float nq = sq3(qx, qy, qz);
+  int* o = out + ((size_t)b * S + warp) * nsample;
+  int cnt = 0, first = -1;
+  for (int i0 = 0; i0 < N && cnt < nsample; i0 += 32) {
+    int i = i0 + lane;
+    bool in = false;
+    if (i < N) {
+      float x = xb[i], y = xb[N + i], z = xb[2 * N + i];
+      float d = sqdist_expanded(dot3(qx, qy, qz, x, y, z), nq, sq3(x, y, z));
+      in = !(d > r2);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, in);
+    if (first < 0 && m != 0) first = i0 + __ffs(m) - 1;
+    int pos = cnt + __popc(m & ((1u << lane) - 1));
+    if (in && pos < nsample) o[pos] = i;
+    cnt += __popc(m);
+  }
+  if (cnt > nsample) cnt = nsample;
+  if (first < 0) first = 0;
+  for (int p = cnt + lane; p < nsample; p += 32) o[p] = first;
+}
+
+// ---- nsample nearest points of every query, ascending: bitonic sort of (d, i) in shared memory ---
+__global__ void __launch_bounds__(512)
+knn_query_kernel(const float* __restrict__ xyz, const float* __restrict__ query, int N, int S, int NP2, int nsample,
+                 int* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* kv = sm;                                  // [NP2]
+  int* ki = reinterpret_cast<int*>(sm + NP2);      // [NP2]
+  const int s = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+  const float* xb = xyz + (size_t)b * 3 * N;
+  const float* qb = query + (size_t)b * 3 * S;
+  const float qx = qb[s], qy = qb[S + s], qz = qb[2 * S + s];
+  const float nq = sq3(qx, qy, qz);
+  for (int i = tid; i < NP2; i += nt) {
+    float d = INFINITY;
+    if (i < N) {
+      float x = xb[i], y = xb[N + i], z = xb[2 * N + i];
+      d = sqdist_expanded(dot3(qx, qy, qz, x, y, z), nq, sq3(x, y, z));
+    }
+    kv[i] = d;
+    ki[i] = i;
+  }
+  __syncthreads();
+  for (int size = 2; size <= NP2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (NP2 >> 1); t += nt) {
+        int lo = (t / stride) * stride * 2 + (t % stride);
+        int hi = lo + stride;
+        bool asc = ((lo & size) == 0);
+        float a = kv[lo], c = kv[hi];
+        int ai = ki[lo], ci = ki[hi];
+        bool gt = (a > c) || (a == c && ai > ci);
+        if (gt == asc) { kv[lo] = c; kv[hi] = a; ki[lo] = ci; ki[hi] = ai; }
+      }
+      __syncthreads();
+    }
+  }
+  int* o = out + ((size_t)b * S + s) * nsample;
+  for (int p = tid; p < nsample; p += nt) o[p] = ki[p];
+}
+
+// ---- k (<= 8) nearest nodes of every point, ascending --------------------------------------------
+__global__ void __launch_bounds__(256)
+three_nn_kernel(const float* __restrict__ xyz, const float* __restrict__ nodes, int N, int M, int k,
+                int* __restrict__ out) {
+  extern __shared__ float sm[];  // nodes x,y,z,|.|^2 : [4][M]
+  const int b = blockIdx.y;
+  const float* nb = nodes + (size_t)b * 3 * M;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    float x = nb[j], y = nb[M + j], z = nb[2 * M + j];
+    sm[j] = x; sm[M + j] = y; sm[2 * M + j] = z; sm[3 * M + j] = sq3(x, y, z);
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* xb = xyz + (size_t)b * 3 * N;
+  const float x = xb[i], y = xb[N + i], z = xb[2 * N + i];
+  const float np = sq3(x, y, z);
+  float bd[8];
+  int bi[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { bd[u] = INFINITY; bi[u] = 0x7fffffff; }
+  for (int j = 0; j < M; ++j) {
+    float d = sqdist_expanded(dot3(x, y, z, sm[j], sm[M + j], sm[2 * M + j]), np, sm[3 * M + j]);
+    int jj = j;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (u < k && (d < bd[u] || (d == bd[u] && jj < bi[u]))) {
+        float td = bd[u]; int ti = bi[u];
+        bd[u] = d; bi[u] = jj;
+        d = td; jj = ti;
+      }
+    }
+  }
+  int* o = out + ((size_t)b * N + i) * k;
+  for (int u = 0; u < k; ++u) o[u] = bi[u];
+}
+
+}  // namespace sug
+
+using namespace sug;
+
+extern "C" int sug_fps(const float* xyz, int B, int N, int npoint, const int32_t* start, int32_t* out_idx,
+                       sug_stream_t stream) {
+  SUG_CHECK_ARG(xyz && start && out_idx, "fps: null pointer");
+  SUG_CHECK_ARG(B > 0 && N > 0 && npoint > 0, "fps: bad shape");
+  size_t smem = sizeof(float) * 4 * (size_t)N;
+  SUG_CHECK_ARG(smem <= 227 * 1024, "fps: N=%d needs %zu B of shared memory", N, smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SUG_CUDA(cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int nt = N >= 1024 ? 1024 : ((N + 31) / 32) * 32;
+  fps_kernel<<<B, nt, smem, (cudaStream_t)stream>>>(xyz, N, npoint, start, out_idx);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_ball_query(const float* xyz, const float* query, int B, int N, int S, float radius, int nsample,
+                              int32_t* out_idx, sug_stream_t stream) {
+  SUG_CHECK_ARG(xyz && query && out_idx, "ball_query: null pointer");
+  SUG_CHECK_ARG(B > 0 && N > 0 && S > 0 && nsample > 0, "ball_query: bad shape");
+  const float r2 = (float)((double)radius * (double)radius);
+  dim3 grid(cdiv((long long)S * 32, 256), B);
+  ball_query_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyz, query, N, S, r2, nsample, out_idx);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_knn_query(const float* xyz, const float* query, int B, int N, int S, int nsample, int32_t* out_idx,
+                             sug_stream_t stream) {
+  SUG_CHECK_ARG(xyz && query && out_idx, "knn_query: null pointer");
+  SUG_CHECK_ARG(B > 0 && N > 0 && S > 0 && nsample > 0 && nsample <= N, "knn_query: bad shape");
+  int np2 = 2;
+  while (np2 < N) np2 <<= 1;
+  size_t smem = 8 * (size_t)np2;
+  SUG_CHECK_ARG(smem <= 227 * 1024, "knn_query: N=%d too large", N);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SUG_CUDA(cudaFuncSetAttribute(knn_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int nt = np2 / 2 < 512 ? (np2 / 2 < 32 ? 32 : np2 / 2) : 512;
+  knn_query_kernel<<<dim3(S, B), nt, smem, (cudaStream_t)stream>>>(xyz, query, N, S, np2, nsample, out_idx);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_three_nn(const float* xyz, const float* nodes, int B, int N, int M, int k, int32_t* out_idx,
+                            sug_stream_t stream) {
+  SUG_CHECK_ARG(xyz && nodes && out_idx, "three_nn: null pointer");
+  SUG_CHECK_ARG(B > 0 && N > 0 && M > 0 && k > 0 && k <= 8 && k <= M, "three_nn: bad shape");
+  size_t smem = sizeof(float) * 4 * (size_t)M;
+  SUG_CHECK_ARG(smem <= 48 * 1024, "three_nn: M=%d too large", M);
+  three_nn_kernel<<<dim3(cdiv(N, 256), B), 256, smem, (cudaStream_t)stream>>>(xyz, nodes, N, M, k, out_idx);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,102 @@
+// Shared helpers for libsug_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <float.h>
+#include <math.h>
+
+#include "../../include/sug_b200.h"
+
+namespace sug {
+
+void set_error(const char* fmt, ...);
+
+#define SUG_CHECK_ARG(cond, ...)                \
+  do {                                          \
+    if (!(cond)) {                              \
+      sug::set_error(__VA_ARGS__);              \
+      return SUG_E_BADARG;                      \
+    }                                           \
+  } while (0)
+
+#define SUG_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      sug::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                     __LINE__);                                                          \
+      return (int)_e;                                                                    \
+    }                                                                                    \
+  } while (0)
+
+#define SUG_LAUNCH_CHECK()                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess) {                                                                 \
+      sug::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__,   \
+                     __LINE__);                                                              \
+      return (int)_e;                                                                        \
+    }                                                                                        \
+  } while (0)
+
+#define SUG_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != 0) return _r;    \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int num_sms();
+
+// Simple bump allocator over the caller's workspace.
+struct Workspace {
+  char* base;
+  size_t size;
+  size_t off;
+  Workspace(void* p, size_t n) : base((char*)p), size(n), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t o = align_up(off, 256);
+    size_t need = o + count * sizeof(T);
+    if (base == nullptr || need > size) {
+      off = (size_t)-1;
+      return nullptr;
+    }
+    off = need;
+    return (T*)(base + o);
+  }
+  bool ok() const { return off != (size_t)-1; }
+};
+
+// ---- device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float act_leaky(float z, float slope) { return z > 0.f ? z : z * slope; }
+__device__ __forceinline__ float act_leaky_grad(float z, float slope) { return z > 0.f ? 1.f : slope; }
+
+// internal launchers shared between translation units -----------------------------------------
+int gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
+             const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
+             cudaStream_t stream);
+
+// Per-channel BatchNorm batch statistics -> (mean, invstd), running-stat update.
+// sums: [2*C] doubles (sum, sum of squares) over `count` samples.
+int bn_finalize_stats(const double* sums, int C, double count, float eps, float momentum,
+                      float* running_mean, float* running_var, float* save_mean_invstd,
+                      cudaStream_t stream);
+// (mean, invstd) from running statistics (eval mode).
+int bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
+                  float* save_mean_invstd, cudaStream_t stream);
+
+}  // namespace sug

@@ -1,0 +1,416 @@
+// EdgeConv with exact train-mode BatchNorm, without ever forming the [B,2C,N,k] edge tensor.
+// Reference: model/model_utils.py:188-210 (get_graph_feature), 8-32 (conv_2d), Model.py:88-109.
+//
+//   y_ij = W [x_j - x_i ; x_i] = a_j + b_i,   a = W1 x,  b = (W2 - W1) x          (per-point GEMM)
+//   ext_i = max_j y_ij (min_j where gamma < 0),  S_i = sum_j y_ij,  sum / sum^2 over all edges
+//   out_i = LeakyReLU(gamma (ext_i - mean) invstd + beta)     (BN affine o LeakyReLU is monotone)
+//
+// Backward: with ghat_i = g_i LReLU'(z_i), G1 = sum ghat, G2 = sum ghat yhat*,
+//   dL/dy_ij = scale [ ghat_i [j = j*_i] - G1/M - yhat_ij G2/M ],  scale = gamma invstd, M = B N k
+//   dB_i = scale [ ghat_i - k G1/M - (G2/M) invstd (S_i - k mean) ]
+//   dA_j = scale [ sum_{(i,s) -> j, arg_i = s} ghat_i - deg_j G1/M
+//                  - (G2/M) invstd (deg_j (a_j - mean) + sum_{i -> j} b_i) ]
+// evaluated as a gather over the transposed neighbour graph (no atomics, deterministic).
+#include "common.cuh"
+
+namespace sug {
+
+__global__ void edge_pack_weight_kernel(const float* __restrict__ w, int C, int Cout, float* __restrict__ wcat) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Cout * C) return;
+  int o = e / C, c = e % C;
+  float w1 = w[(size_t)o * 2 * C + c];
+  float w2 = w[(size_t)o * 2 * C + C + c];
+  wcat[(size_t)o * C + c] = w1;
+  wcat[(size_t)(Cout + o) * C + c] = w2 - w1;
+}
+
+__global__ void edge_unpack_wgrad_kernel(const float* __restrict__ dwcat, int C, int Cout, float* __restrict__ dw) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Cout * C) return;
+  int o = e / C, c = e % C;
+  float da = dwcat[(size_t)o * C + c];
+  float db = dwcat[(size_t)(Cout + o) * C + c];
+  dw[(size_t)o * 2 * C + c] = da - db;
+  dw[(size_t)o * 2 * C + C + c] = db;
+}
+
+// One thread per (point, 4 channels).  TRAIN: writes ext/arg/ssum and accumulates the BN sums.
+// !TRAIN: statistics are known (running), so the activation is applied here and `out` written.
+template <bool TRAIN>
+__global__ void __launch_bounds__(256)
+edge_gather_fwd_kernel(const float* __restrict__ ab, const int* __restrict__ idx, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ mean_invstd, int P, int N, int k,
+                       int Cout, float slope, float* __restrict__ ext, uint8_t* __restrict__ arg,
+                       float* __restrict__ ssum, double* __restrict__ sums, float* __restrict__ out, long long ldo) {
+  __shared__ double red[256][8];
+  const int CQ = Cout >> 2;
+  const int PPB = 256 / CQ;
+  const int tid = threadIdx.x;
+  const int pl = tid / CQ, c4 = tid - pl * CQ;
+  const bool active = pl < PPB;
+  const int ld = 2 * Cout;
+  float sgn[4], sc[4], sh[4];
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float g = __ldg(gamma + 4 * c4 + u);
+      sgn[u] = g < 0.f ? -1.f : 1.f;
+      if (!TRAIN) {
+        float m = __ldg(mean_invstd + 4 * c4 + u), is = __ldg(mean_invstd + Cout + 4 * c4 + u);
+        sc[u] = g * is;
+        sh[u] = __ldg(beta + 4 * c4 + u) - m * sc[u];
+      }
+    }
+  }
+  double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+  for (long long p0 = (long long)blockIdx.x * PPB; p0 < P; p0 += (long long)gridDim.x * PPB) {
+    const long long i = p0 + pl;
+    if (!active || i >= P) continue;
+    const long long cb = (i / N) * N;
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ab + i * ld + Cout) + c4);
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bslot[4] = {0, 0, 0, 0};
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    const int* ip = idx + i * k;
+    for (int s0 = 0; s0 < k; s0 += 4) {
+      float4 a4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int s = min(s0 + u, k - 1);
+        long long j = cb + __ldg(ip + s);
+        a4[u] = __ldg(reinterpret_cast<const float4*>(ab + j * ld) + c4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (s0 + u >= k) break;
+        const float aa[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float y = aa[v] + bb[v];
+          float ys = y * sgn[v];
+          if (ys > best[v]) { best[v] = ys; bslot[v] = s0 + u; }
+          if (TRAIN) {
+            s1[v] += y;
+            s2[v] = fmaf(y, y, s2[v]);
+          }
+        }
+      }
+    }
+    float e[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) e[v] = best[v] * sgn[v];
+    if (TRAIN) {
+      reinterpret_cast<float4*>(ext + i * Cout)[c4] = make_float4(e[0], e[1], e[2], e[3]);
+      reinterpret_cast<float4*>(ssum + i * Cout)[c4] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+      reinterpret_cast<uchar4*>(arg + i * Cout)[c4] =
+          make_uchar4((unsigned char)bslot[0], (unsigned char)bslot[1], (unsigned char)bslot[2], (unsigned char)bslot[3]);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        ds[v] += (double)s1[v];
+        dq[v] += (double)s2[v];
+      }
+    } else {
+      float4 o;
+      o.x = act_leaky(fmaf(sc[0], e[0], sh[0]), slope);
+      o.y = act_leaky(fmaf(sc[1], e[1], sh[1]), slope);
+      o.z = act_leaky(fmaf(sc[2], e[2], sh[2]), slope);
+      o.w = act_leaky(fmaf(sc[3], e[3], sh[3]), slope);
+      *reinterpret_cast<float4*>(out + i * ldo + 4 * c4) = o;
+    }
+  }
+  if (TRAIN) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      red[tid][v] = ds[v];
+      red[tid][4 + v] = dq[v];
+    }
+    __syncthreads();
+    if (active && pl == 0) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        double a = 0, q = 0;
+        for (int r = 0; r < PPB; ++r) {
+          a += red[r * CQ + c4][v];
+          q += red[r * CQ + c4][4 + v];
+        }
+        atomicAdd(&sums[4 * c4 + v], a);
+        atomicAdd(&sums[Cout + 4 * c4 + v], q);
+      }
+    }
+  }
+}
+
+// out = act(gamma (ext - mean) invstd + beta), float4 per thread.
+__global__ void __launch_bounds__(256)
+bn_act_kernel(const float* __restrict__ ext, const float* __restrict__ gamma, const float* __restrict__ beta,
+              const float* __restrict__ mean_invstd, long long P, int Cout, float slope, float* __restrict__ out,
+              long long ldo) {
+  extern __shared__ float ss[];  // scale[Cout], shift[Cout]
+  for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
+    float sc = gamma[c] * mean_invstd[Cout + c];
+    ss[c] = sc;
+    ss[Cout + c] = beta[c] - mean_invstd[c] * sc;
+  }
+  __syncthreads();
+  const int CQ = Cout >> 2;
+  const long long total = P * CQ;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long i = e / CQ;
+    int c4 = (int)(e - i * CQ);
+    float4 v = __ldg(reinterpret_cast<const float4*>(ext + i * Cout) + c4);
+    const float* sc = ss + 4 * c4;
+    const float* sh = ss + Cout + 4 * c4;
+    float4 o;
+    o.x = act_leaky(fmaf(sc[0], v.x, sh[0]), slope);
+    o.y = act_leaky(fmaf(sc[1], v.y, sh[1]), slope);
+    o.z = act_leaky(fmaf(sc[2], v.z, sh[2]), slope);
+    o.w = act_leaky(fmaf(sc[3], v.w, sh[3]), slope);
+    *reinterpret_cast<float4*>(out + i * ldo + 4 * c4) = o;
+  }
+}
+
+// ghat = g * act'(z);  G1 += ghat;  G2 += ghat * yhat.
+__global__ void __launch_bounds__(256)
+edge_bwd_pre_kernel(const float* __restrict__ gout, long long ldg, const float* __restrict__ ext,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ mean_invstd, long long P, int Cout, float slope,
+                    float* __restrict__ ghat, double* __restrict__ gsums) {
+  __shared__ double red[256][8];
+  const int CQ = Cout >> 2;
+  const int PPB = 256 / CQ;
+  const int tid = threadIdx.x;
+  const int pl = tid / CQ, c4 = tid - pl * CQ;
+  const bool active = pl < PPB;
+  float mean[4], is[4], sc[4], sh[4];
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int c = 4 * c4 + u;
+      mean[u] = __ldg(mean_invstd + c);
+      is[u] = __ldg(mean_invstd + Cout + c);
+      sc[u] = __ldg(gamma + c) * is[u];
+      sh[u] = __ldg(beta + c) - mean[u] * sc[u];
+    }
+  }
+  double g1[4] = {0, 0, 0, 0}, g2[4] = {0, 0, 0, 0};
+  for (long long p0 = (long long)blockIdx.x * PPB; p0 < P; p0 += (long long)gridDim.x * PPB) {
+    const long long i = p0 + pl;
+    if (!active || i >= P) continue;
+    float4 g = __ldg(reinterpret_cast<const float4*>(gout + i * ldg) + c4);
+    float4 e = __ldg(reinterpret_cast<const float4*>(ext + i * Cout) + c4);
+    const float gg[4] = {g.x, g.y, g.z, g.w};
+    const float ee[4] = {e.x, e.y, e.z, e.w};
+    float gh[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float z = fmaf(sc[u], ee[u], sh[u]);
+      gh[u] = gg[u] * act_leaky_grad(z, slope);
+      g1[u] += (double)gh[u];
+      g2[u] += (double)(gh[u] * ((ee[u] - mean[u]) * is[u]));
+    }
+    reinterpret_cast<float4*>(ghat + i * Cout)[c4] = make_float4(gh[0], gh[1], gh[2], gh[3]);
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    red[tid][v] = g1[v];
+    red[tid][4 + v] = g2[v];
+  }
+  __syncthreads();
+  if (active && pl == 0) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      double a = 0, q = 0;
+      for (int r = 0; r < PPB; ++r) {
+        a += red[r * CQ + c4][v];
+        q += red[r * CQ + c4][4 + v];
+      }
+      atomicAdd(&gsums[4 * c4 + v], a);
+      atomicAdd(&gsums[Cout + 4 * c4 + v], q);
+    }
+  }
+}
+
+// dA | dB per point from the transposed graph.
+__global__ void __launch_bounds__(256)
+edge_bwd_main_kernel(const float* __restrict__ ab, const float* __restrict__ ghat, const uint8_t* __restrict__ arg,
+                     const float* __restrict__ ssum, const int* __restrict__ rev_ptr, const int* __restrict__ rev_edge,
+                     const float* __restrict__ gamma, const float* __restrict__ mean_invstd,
+                     const double* __restrict__ gsums, long long P, int N, int k, int Cout, float* __restrict__ dab,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int CQ = Cout >> 2;
+  const int PPB = 256 / CQ;
+  const int tid = threadIdx.x;
+  const int pl = tid / CQ, c4 = tid - pl * CQ;
+  if (pl >= PPB) return;
+  const int ld = 2 * Cout;
+  const double Md = (double)P * (double)k;
+  float mean[4], is[4], sc[4], c1[4], c2[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    int c = 4 * c4 + u;
+    mean[u] = __ldg(mean_invstd + c);
+    is[u] = __ldg(mean_invstd + Cout + c);
+    sc[u] = __ldg(gamma + c) * is[u];
+    double G1 = gsums[c], G2 = gsums[Cout + c];
+    c1[u] = (float)(G1 / Md);
+    c2[u] = (float)(G2 / Md) * is[u];
+    if (blockIdx.x == 0 && pl == 0) {
+      dbeta[c] = (float)G1;
+      dgamma[c] = (float)G2;
+    }
+  }
+  const float kf = (float)k;
+  for (long long p0 = (long long)blockIdx.x * PPB; p0 < P; p0 += (long long)gridDim.x * PPB) {
+    const long long j = p0 + pl;
+    if (j >= P) continue;
+    const long long bidx = j / N;
+    const long long cb = bidx * N;
+    const int jl = (int)(j - cb);
+    const int* rp = rev_ptr + bidx * (N + 1);
+    const int lo = __ldg(rp + jl), hi = __ldg(rp + jl + 1);
+    const int* re = rev_edge + cb * k;
+    float T[4] = {0, 0, 0, 0}, Gs[4] = {0, 0, 0, 0};
+    for (int t = lo; t < hi; ++t) {
+      int pk = __ldg(re + t);
+      long long i = cb + (pk >> 8);
+      unsigned s = (unsigned)(pk & 255);
+      float4 b4 = __ldg(reinterpret_cast<const float4*>(ab + i * ld + Cout) + c4);
+      float4 g4 = __ldg(reinterpret_cast<const float4*>(ghat + i * Cout) + c4);
+      uchar4 a4 = __ldg(reinterpret_cast<const uchar4*>(arg + i * Cout) + c4);
+      T[0] += b4.x; T[1] += b4.y; T[2] += b4.z; T[3] += b4.w;
+      Gs[0] += (a4.x == s) ? g4.x : 0.f;
+      Gs[1] += (a4.y == s) ? g4.y : 0.f;
+      Gs[2] += (a4.z == s) ? g4.z : 0.f;
+      Gs[3] += (a4.w == s) ? g4.w : 0.f;
+    }
+    const float deg = (float)(hi - lo);
+    float4 a4 = __ldg(reinterpret_cast<const float4*>(ab + j * ld) + c4);
+    float4 gh = __ldg(reinterpret_cast<const float4*>(ghat + j * Cout) + c4);
+    float4 S4 = __ldg(reinterpret_cast<const float4*>(ssum + j * Cout) + c4);
+    const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+    const float gg[4] = {gh.x, gh.y, gh.z, gh.w};
+    const float SS[4] = {S4.x, S4.y, S4.z, S4.w};
+    float dA[4], dB[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      dB[u] = sc[u] * (gg[u] - kf * c1[u] - c2[u] * (SS[u] - kf * mean[u]));
+      dA[u] = sc[u] * (Gs[u] - deg * c1[u] - c2[u] * (deg * (aa[u] - mean[u]) + T[u]));
+    }
+    reinterpret_cast<float4*>(dab + j * ld)[c4] = make_float4(dA[0], dA[1], dA[2], dA[3]);
+    reinterpret_cast<float4*>(dab + j * ld + Cout)[c4] = make_float4(dB[0], dB[1], dB[2], dB[3]);
+  }
+}
+
+static int gather_grid(long long P, int Cout) {
+  int ppb = 256 / (Cout >> 2);
+  long long blocks = (P + ppb - 1) / ppb;
+  long long cap = (long long)num_sms() * 8;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace sug
+
+using namespace sug;
+
+extern "C" size_t sug_edgeconv_ws_bytes(int B, int N, int C, int Cout, int k) {
+  (void)k;
+  size_t P = (size_t)B * N;
+  size_t w = align_up(sizeof(float) * 2 * (size_t)Cout * C, 256);
+  size_t s = align_up(sizeof(double) * 2 * (size_t)Cout, 256);
+  size_t gh = align_up(sizeof(float) * P * Cout, 256);
+  return 2 * w + s + gh + 1024;
+}
+
+static int edge_check(int B, int N, int C, int Cout, int k) {
+  SUG_CHECK_ARG(B > 0 && N > 0 && C > 0, "edgeconv: bad shape B=%d N=%d C=%d", B, N, C);
+  SUG_CHECK_ARG(Cout % 4 == 0 && Cout >= 4 && Cout <= 1024, "edgeconv: Cout=%d must be a multiple of 4 in [4,1024]", Cout);
+  SUG_CHECK_ARG(k > 0 && k <= 255, "edgeconv: k=%d out of range", k);
+  return 0;
+}
+
+extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx, const float* w, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, int B, int N, int C,
+                                int Cout, int k, float eps, float momentum, float slope, int training, float* out,
+                                int64_t ldo, float* ab, float* ext, uint8_t* arg, float* ssum,
+                                float* save_mean_invstd, void* ws, size_t ws_bytes, sug_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SUG_TRY(edge_check(B, N, C, Cout, k));
+  SUG_CHECK_ARG(x && idx && w && gamma && beta && out && ab, "edgeconv_fwd: null pointer");
+  SUG_CHECK_ARG(ldo % 4 == 0 && ((uintptr_t)out % 16) == 0, "edgeconv_fwd: out must be 16B aligned with ldo %% 4 == 0");
+  SUG_CHECK_ARG(running_mean && running_var, "edgeconv_fwd: running statistics required");
+  if (training) SUG_CHECK_ARG(ext && arg && ssum && save_mean_invstd, "edgeconv_fwd: training needs ext/arg/ssum/save");
+  const long long P = (long long)B * N;
+  Workspace W(ws, ws_bytes);
+  float* wcat = W.take<float>(2 * (size_t)Cout * C);
+  double* sums = W.take<double>(2 * (size_t)Cout);
+  float* mi_eval = W.take<float>(2 * (size_t)Cout);
+  if (!W.ok()) { set_error("edgeconv_fwd: workspace too small (%zu B)", ws_bytes); return SUG_E_WORKSPACE; }
+
+  edge_pack_weight_kernel<<<cdiv((long long)Cout * C, 256), 256, 0, stream>>>(w, C, Cout, wcat);
+  SUG_LAUNCH_CHECK();
+  SUG_TRY(gemm_f32(x, ldx, 1, wcat, C, 1, nullptr, ab, 2 * Cout, (int)P, 2 * Cout, C, 0, stream));
+  const int grid = gather_grid(P, Cout);
+  if (training) {
+    SUG_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cout, stream));
+    edge_gather_fwd_kernel<true><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, nullptr, (int)P, N, k, Cout, slope,
+                                                           ext, arg, ssum, sums, nullptr, 0);
+    SUG_LAUNCH_CHECK();
+    SUG_TRY(bn_finalize_stats(sums, Cout, (double)P * k, eps, momentum, running_mean, running_var,
+                              save_mean_invstd, stream));
+    long long total = P * (Cout >> 2);
+    int g2 = (int)min((long long)num_sms() * 8, (total + 255) / 256);
+    bn_act_kernel<<<g2, 256, 2 * Cout * sizeof(float), stream>>>(ext, gamma, beta, save_mean_invstd, P, Cout, slope,
+                                                                 out, ldo);
+    SUG_LAUNCH_CHECK();
+  } else {
+    SUG_TRY(bn_eval_stats(running_mean, running_var, Cout, eps, mi_eval, stream));
+    edge_gather_fwd_kernel<false><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, mi_eval, (int)P, N, k, Cout, slope,
+                                                            nullptr, nullptr, nullptr, nullptr, out, ldo);
+    SUG_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int sug_edgeconv_bwd(const float* gout, int64_t ldg, const float* x, int64_t ldx, const int32_t* idx,
+                                const int32_t* rev_ptr, const int32_t* rev_edge, const float* w, const float* gamma,
+                                const float* beta, const float* ab, const float* ext, const uint8_t* arg,
+                                const float* ssum, const float* save_mean_invstd, int B, int N, int C, int Cout, int k,
+                                float slope, float* dx, int64_t lddx, int accumulate_dx, float* dw, float* dgamma,
+                                float* dbeta, float* dab, void* ws, size_t ws_bytes, sug_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  (void)idx;
+  SUG_TRY(edge_check(B, N, C, Cout, k));
+  SUG_CHECK_ARG(gout && x && rev_ptr && rev_edge && w && gamma && beta && ab && ext && arg && ssum &&
+                    save_mean_invstd && dw && dgamma && dbeta && dab,
+                "edgeconv_bwd: null pointer");
+  SUG_CHECK_ARG(ldg % 4 == 0 && ((uintptr_t)gout % 16) == 0, "edgeconv_bwd: gout must be 16B aligned with ldg %% 4 == 0");
+  const long long P = (long long)B * N;
+  Workspace W(ws, ws_bytes);
+  float* wcat = W.take<float>(2 * (size_t)Cout * C);
+  float* dwcat = W.take<float>(2 * (size_t)Cout * C);
+  double* gsums = W.take<double>(2 * (size_t)Cout);
+  float* ghat = W.take<float>((size_t)P * Cout);
+  if (!W.ok()) { set_error("edgeconv_bwd: workspace too small (%zu B)", ws_bytes); return SUG_E_WORKSPACE; }
+
+  SUG_CUDA(cudaMemsetAsync(gsums, 0, sizeof(double) * 2 * Cout, stream));
+  const int grid = gather_grid(P, Cout);
+  edge_bwd_pre_kernel<<<grid, 256, 0, stream>>>(gout, ldg, ext, gamma, beta, save_mean_invstd, P, Cout, slope, ghat,
+                                                gsums);
+  SUG_LAUNCH_CHECK();
+  edge_bwd_main_kernel<<<grid, 256, 0, stream>>>(ab, ghat, arg, ssum, rev_ptr, rev_edge, gamma, save_mean_invstd,
+                                                 gsums, P, N, k, Cout, dab, dgamma, dbeta);
+  SUG_LAUNCH_CHECK();
+  // dWcat = dab^T x   ([2Cout, P] x [P, C])
+  SUG_TRY(gemm_f32(dab, 1, 2 * Cout, x, 1, ldx, nullptr, dwcat, C, 2 * Cout, C, (int)P, 0, stream));
+  edge_unpack_wgrad_kernel<<<cdiv((long long)Cout * C, 256), 256, 0, stream>>>(dwcat, C, Cout, dw);
+  SUG_LAUNCH_CHECK();
+  if (dx != nullptr) {
+    edge_pack_weight_kernel<<<cdiv((long long)Cout * C, 256), 256, 0, stream>>>(w, C, Cout, wcat);
+    SUG_LAUNCH_CHECK();
+    // dx = dab * Wcat   ([P, 2Cout] x [2Cout, C])
+    SUG_TRY(gemm_f32(dab, 2 * Cout, 1, wcat, 1, C, nullptr, dx, lddx, (int)P, C, 2 * Cout, accumulate_dx, stream));
+  }
+  return 0;
+}

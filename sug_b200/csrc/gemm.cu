@@ -1,0 +1,146 @@
+// Exact-fp32 CUDA-core GEMM: C[M,N] (+)= A * B^T (+ bias).
+//
+// Used for the xyz layer (K = 3 / 6, where tensor cores have nothing to do), for the narrow
+// weight-gradient reductions, and as the in-library fp32 reference of the tcgen05 path.
+// 128x128x8 tiles, 256 threads, 8x8 outputs per thread (split 4+4 so that every LDS.128 of a
+// quarter-warp is contiguous), double-buffered shared memory with register prefetch.
+// Operands are addressed with generic (row, k) strides so the same kernel serves
+//   X * W^T            (both k-contiguous)            forward per-point GEMM
+//   dY * W             (A k-contiguous, B n-contiguous) input gradient
+//   dY^T * X           (both k-strided, split-K)        weight gradient
+#include "common.cuh"
+
+namespace sug {
+
+constexpr int GBM = 128, GBN = 128, GBK = 8, GPAD = 4;
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256, 2)
+gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ Bm,
+                 long long sbn, long long sbk, const float* __restrict__ bias, float* __restrict__ C,
+                 long long ldc, int M, int N, int K, int kchunk, int accumulate, int use_atomic) {
+  __shared__ __align__(16) float As[2][GBK][GBM + GPAD];
+  __shared__ __align__(16) float Bs[2][GBK][GBN + GPAD];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(K, kbeg + kchunk);
+  const int tx = tid & 15, ty = tid >> 4;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float ra[4], rb[4];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + i * 256;
+      int mm, kk;
+      if (A_KC) { kk = e % GBK; mm = e / GBK; } else { mm = e % GBM; kk = e / GBM; }
+      int gm = m0 + mm, gk = k0 + kk;
+      ra[i] = (gm < M && gk < kend) ? __ldg(A + (long long)gm * sam + (long long)gk * sak) : 0.f;
+      int nn, kb;
+      if (B_KC) { kb = e % GBK; nn = e / GBK; } else { nn = e % GBN; kb = e / GBN; }
+      int gn = n0 + nn, gkb = k0 + kb;
+      rb[i] = (gn < N && gkb < kend) ? __ldg(Bm + (long long)gn * sbn + (long long)gkb * sbk) : 0.f;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + i * 256;
+      int mm, kk;
+      if (A_KC) { kk = e % GBK; mm = e / GBK; } else { mm = e % GBM; kk = e / GBM; }
+      As[buf][kk][mm] = ra[i];
+      int nn, kb;
+      if (B_KC) { kb = e % GBK; nn = e / GBK; } else { nn = e % GBN; kb = e / GBN; }
+      Bs[buf][kb][nn] = rb[i];
+    }
+  };
+
+  if (kbeg < kend) {
+    load_tile(kbeg);
+    store_tile(0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += GBK, buf ^= 1) {
+    const bool has_next = k0 + GBK < kend;
+    if (has_next) load_tile(k0 + GBK);
+#pragma unroll
+    for (int kk = 0; kk < GBK; ++kk) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (has_next) store_tile(buf ^ 1);
+    __syncthreads();
+  }
+
+  const bool add_bias = bias != nullptr && blockIdx.z == 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (add_bias) v += __ldg(bias + gn);
+      float* p = C + (long long)gm * ldc + gn;
+      if (use_atomic) atomicAdd(p, v);
+      else if (accumulate) *p += v;
+      else *p = v;
+    }
+  }
+}
+
+int gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
+             const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
+             cudaStream_t stream) {
+  SUG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  SUG_CHECK_ARG(a && b && c, "gemm: null operand");
+  const int tm = cdiv(M, GBM), tn = cdiv(N, GBN);
+  const long long tiles = (long long)tm * tn;
+  int splits = 1;
+  if (tiles < num_sms() && K >= 1024) {
+    splits = (int)min((long long)cdiv(K, 512), (2LL * num_sms() + tiles - 1) / tiles);
+    if (splits < 1) splits = 1;
+  }
+  int kchunk = cdiv(cdiv(K, splits), GBK) * GBK;
+  splits = cdiv(K, kchunk);
+  const int use_atomic = splits > 1;
+  if (use_atomic && !accumulate)
+    SUG_CUDA(cudaMemset2DAsync(c, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
+  dim3 grid(tn, tm, splits);
+  const bool akc = (sak == 1), bkc = (sbk == 1);
+#define SUG_GEMM_LAUNCH(AK, BK_)                                                                             \
+  gemm_simt_kernel<AK, BK_><<<grid, 256, 0, stream>>>(a, sam, sak, b, sbn, sbk, bias, c, ldc, M, N, K, kchunk, \
+                                                      accumulate, use_atomic)
+  if (akc && bkc) SUG_GEMM_LAUNCH(true, true);
+  else if (akc) SUG_GEMM_LAUNCH(true, false);
+  else if (bkc) SUG_GEMM_LAUNCH(false, true);
+  else SUG_GEMM_LAUNCH(false, false);
+#undef SUG_GEMM_LAUNCH
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sug
+
+extern "C" int sug_gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
+                            const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
+                            sug_stream_t stream) {
+  return sug::gemm_f32(a, sam, sak, b, sbn, sbk, bias, c, ldc, M, N, K, accumulate, (cudaStream_t)stream);
+}

@@ -1,0 +1,171 @@
+// Multi-kernel Gaussian MMD (reference: model/mmd.py:239-312, mix_rbf_mmd2 / _mix_rbf_kernel / _mmd2)
+// and the Chamfer distance used by the SDA geometric weights (mmd.py:126-128,169-175).
+//
+// loss = sum_ij c_ij K_ij,  K_ij = sum_sigma exp(-E_ij / (2 sigma^2)),  E_ij = G_ii + G_jj - 2 G_ij,
+// G = Z Z^T.  The squared norms are read from the Gram diagonal exactly like the reference, so the
+// exponent on the diagonal is exactly 0 (with sigma = 0.01 a 1e-3 error there changes K by e^{+-5}).
+//   biased:   c = 1/m^2 on XX and YY, -w_j/m^2 on XY and YX (w = SDA column weights, mmd.py:293-297)
+//   unbiased: c = 1/(m(m-1)) off the diagonal of XX / YY, 0 on it
+// The forward also emits coef = dL/dG so that the backward is one GEMM: dZ = 2 g coef Z.
+#include "common.cuh"
+
+namespace sug {
+
+struct Sigmas {
+  float gamma[8];
+  int n;
+};
+
+__device__ __forceinline__ float mmd_cij(int i, int j, int m, const float* __restrict__ w, int biased) {
+  const bool ix = i < m, jx = j < m;
+  const float mm = (float)m * (float)m;
+  if (ix == jx) {
+    if (biased) return 1.f / mm;
+    return i == j ? 0.f : 1.f / ((float)m * (float)(m - 1));
+  }
+  int col = ix ? j - m : i - m;  // index into Y
+  float wj = w != nullptr ? __ldg(w + col) : 1.f;
+  return -wj / mm;
+}
+
+// one block per row i of the [2m, 2m] kernel matrix
+__global__ void __launch_bounds__(128)
+mmd_coef_kernel(const float* __restrict__ G, int m, Sigmas sg, const float* __restrict__ w, int biased,
+                float* __restrict__ coef, double* __restrict__ acc) {
+  __shared__ double red_l[4], red_q[4];
+  __shared__ float s_qii;
+  const int n2 = 2 * m;
+  const int i = blockIdx.x;
+  const float gii = __ldg(G + (size_t)i * n2 + i);
+  double lsum = 0.0, qsum = 0.0;
+  for (int j = threadIdx.x; j < n2; j += blockDim.x) {
+    const float gjj = __ldg(G + (size_t)j * n2 + j);
+    const float gij = __ldg(G + (size_t)i * n2 + j);
+    const float E = gii - 2.f * gij + gjj;  // mmd.py:247 operation order
+    float K = 0.f, dK = 0.f;
+    for (int s = 0; s < sg.n; ++s) {
+      float e = expf(-sg.gamma[s] * E);
+      K += e;
+      dK = fmaf(-sg.gamma[s], e, dK);
+    }
+    const float c = mmd_cij(i, j, m, w, biased);
+    const float q = c * dK;  // dL/dE_ij
+    lsum += (double)(c * K);
+    qsum += (double)q;
+    if (j == i) s_qii = q;
+    else coef[(size_t)i * n2 + j] = -2.f * q;
+  }
+  lsum = warp_sum(lsum);
+  qsum = warp_sum(qsum);
+  if ((threadIdx.x & 31) == 0) { red_l[threadIdx.x >> 5] = lsum; red_q[threadIdx.x >> 5] = qsum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double l = red_l[0] + red_l[1] + red_l[2] + red_l[3];
+    double q = red_q[0] + red_q[1] + red_q[2] + red_q[3];
+    // E_ii = G_ii + G_ii - 2 G_ii: d/dG_ii collects the row and the column (Q symmetric)
+    coef[(size_t)i * n2 + i] = (float)(2.0 * q - 2.0 * (double)s_qii);
+    atomicAdd(acc, l);
+  }
+}
+
+__global__ void mmd_finalize_kernel(const double* __restrict__ acc, float* __restrict__ loss) { *loss = (float)acc[0]; }
+
+__global__ void scale_rows_kernel(float* __restrict__ d, long long ld, int rows, int cols, const float* __restrict__ g,
+                                  float mul) {
+  const float s = mul * __ldg(g);
+  long long total = (long long)rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long r = e / cols;
+    int c = (int)(e - r * cols);
+    d[r * ld + c] *= s;
+  }
+}
+
+// Squared distance from every point of p to its nearest point of q; tiles of q in shared memory.
+__global__ void __launch_bounds__(128)
+chamfer_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int N, int M, float* __restrict__ d1,
+               float* __restrict__ d2) {
+  __shared__ float sq[128 * 3];
+  const int dir = blockIdx.z;
+  const float* p = dir == 0 ? p1 : p2;
+  const float* q = dir == 0 ? p2 : p1;
+  const int np = dir == 0 ? N : M, nq = dir == 0 ? M : N;
+  float* d = dir == 0 ? d1 : d2;
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (blockIdx.x * 128 >= np) return;
+  const float* pb = p + (size_t)b * np * 3;
+  const float* qb = q + (size_t)b * nq * 3;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (i < np) { x = pb[3 * i]; y = pb[3 * i + 1]; z = pb[3 * i + 2]; }
+  float best = INFINITY;
+  for (int j0 = 0; j0 < nq; j0 += 128) {
+    const int cnt = min(128, nq - j0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * 3; e += 128) sq[e] = qb[(size_t)j0 * 3 + e];
+    __syncthreads();
+    for (int j = 0; j < cnt; ++j) {
+      float dx = x - sq[3 * j], dy = y - sq[3 * j + 1], dz = z - sq[3 * j + 2];
+      float dd = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      best = fminf(best, dd);
+    }
+  }
+  if (i < np) d[(size_t)b * np + i] = best;
+}
+
+}  // namespace sug
+
+using namespace sug;
+
+extern "C" size_t sug_mmd_ws_bytes(int m, int D) {
+  (void)D;
+  return align_up(sizeof(float) * 4 * (size_t)m * m, 256) + 512;
+}
+
+extern "C" int sug_mmd_rbf_fwd(const float* z, int64_t ldz, int m, int D, const float* h_sigmas, int nsig,
+                               const float* weights, int biased, float* loss, float* coef, void* ws, size_t ws_bytes,
+                               sug_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SUG_CHECK_ARG(z && h_sigmas && loss && coef, "mmd_fwd: null pointer");
+  SUG_CHECK_ARG(m > 0 && D > 0 && nsig > 0 && nsig <= 8, "mmd_fwd: bad shape m=%d D=%d nsig=%d", m, D, nsig);
+  SUG_CHECK_ARG(biased || m > 1, "mmd_fwd: unbiased estimate needs m > 1");
+  Workspace W(ws, ws_bytes);
+  float* G = W.take<float>(4 * (size_t)m * m);
+  double* acc = W.take<double>(2);
+  if (!W.ok()) { set_error("mmd_fwd: workspace too small"); return SUG_E_WORKSPACE; }
+  Sigmas sg;
+  sg.n = nsig;
+  for (int s = 0; s < nsig; ++s) sg.gamma[s] = (float)(1.0 / (2.0 * (double)h_sigmas[s] * (double)h_sigmas[s]));
+  const int n2 = 2 * m;
+  SUG_TRY(gemm_f32(z, ldz, 1, z, ldz, 1, nullptr, G, n2, n2, n2, D, 0, stream));
+  SUG_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), stream));
+  mmd_coef_kernel<<<n2, 128, 0, stream>>>(G, m, sg, weights, biased, coef, acc);
+  SUG_LAUNCH_CHECK();
+  mmd_finalize_kernel<<<1, 1, 0, stream>>>(acc, loss);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_mmd_rbf_bwd(const float* z, int64_t ldz, int m, int D, const float* coef, const float* gloss,
+                               float* dz, int64_t lddz, sug_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SUG_CHECK_ARG(z && coef && gloss && dz, "mmd_bwd: null pointer");
+  const int n2 = 2 * m;
+  // dz = coef * z   ([2m, 2m] x [2m, D]),  then scaled by 2 * gloss
+  SUG_TRY(gemm_f32(coef, n2, 1, z, 1, ldz, nullptr, dz, lddz, n2, D, n2, 0, stream));
+  long long total = (long long)n2 * D;
+  scale_rows_kernel<<<(int)min((long long)num_sms() * 4, (total + 255) / 256), 256, 0, stream>>>(dz, lddz, n2, D, gloss,
+                                                                                               2.f);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_chamfer_f32(const float* p1, const float* p2, int B, int N, int M, float* d1, float* d2,
+                               sug_stream_t stream_) {
+  SUG_CHECK_ARG(p1 && p2 && d1 && d2, "chamfer: null pointer");
+  SUG_CHECK_ARG(B > 0 && N > 0 && M > 0, "chamfer: bad shape");
+  dim3 grid(cdiv(N > M ? N : M, 128), B, 2);
+  chamfer_kernel<<<grid, 128, 0, (cudaStream_t)stream_>>>(p1, p2, N, M, d1, d2);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,192 @@
+"""Drop-in for the reference's ``model/model_utils.py`` (same names, signatures and state_dict
+layout), backed by the sm_100a kernels of libsug_b200.
+
+Reference lines are cited per symbol.  Modules keep the reference's attribute structure
+(``conv_2d.conv = Sequential(Conv2d, BatchNorm2d, act)`` etc.) so checkpoints are interchangeable;
+the fused fast paths read their parameters from those sub-modules.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from . import point_utils
+
+
+class conv_2d(nn.Module):
+    """model_utils.py:8-32: Conv2d(kernel) -> BatchNorm2d -> ReLU | Tanh | LeakyReLU(0.01)."""
+
+    def __init__(self, in_ch, out_ch, kernel, activation='relu', bias=True):
+        super().__init__()
+        if activation == 'relu':
+            act = nn.ReLU(inplace=False)
+        elif activation == 'tanh':
+            act = nn.Tanh()
+        elif activation == 'leakyrelu':
+            act = nn.LeakyReLU()
+        else:
+            raise ValueError(f"unsupported activation {activation!r}")
+        self.conv = nn.Sequential(nn.Conv2d(in_ch, out_ch, kernel_size=kernel, bias=bias), nn.BatchNorm2d(out_ch), act)
+
+    def forward(self, x):
+        return self.conv(x)
+
+    # ---- fused fast paths (point-major tensors) -------------------------------------------------
+    def _bn_tick(self):
+        bn = self.conv[1]
+        if self.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        return bn
+
+    def _slope(self):
+        act = self.conv[2]
+        if isinstance(act, nn.LeakyReLU):
+            return float(act.negative_slope)
+        if isinstance(act, nn.ReLU):
+            return 0.0
+        raise RuntimeError("fused paths need a ReLU / LeakyReLU block")
+
+    def edgeconv(self, x_pm, idx):
+        """get_graph_feature(x, idx) -> self -> max over k, without the [B,2C,N,k] tensor.
+        x_pm [B,N,C], idx int32 [B,N,k] -> [B,N,Cout]  (Model.py:88-94)."""
+        conv, bn = self.conv[0], self._bn_tick()
+        if conv.bias is not None:
+            raise RuntimeError("EdgeConv blocks are bias-free in the reference (Model.py:61-64)")
+        return ops.edgeconv(x_pm, idx, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                            self.training, bn.eps, bn.momentum, self._slope())
+
+    def pool_max(self, x_pm):
+        """self -> max over the N points (Model.py:272-274).  x_pm [B,N,Cin] -> [B,Cout]."""
+        conv, bn = self.conv[0], self._bn_tick()
+        return ops.mlp_bn_act_pool(x_pm, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                   self.training, self._slope(), ops.POOL_MAX, bn.eps, bn.momentum)
+
+
+class fc_layer(nn.Module):
+    """model_utils.py:35-57: Linear -> LayerNorm -> ReLU | LeakyReLU(0.2)."""
+
+    def __init__(self, in_ch, out_ch, bn=True, activation='leakyrelu', bias=False):
+        super().__init__()
+        if activation == 'relu':
+            self.ac = nn.ReLU(inplace=False)
+        elif activation == 'leakyrelu':
+            self.ac = nn.LeakyReLU(negative_slope=0.2, inplace=False)
+        if bn:
+            self.fc = nn.Sequential(nn.Linear(in_ch, out_ch, bias=bias), nn.LayerNorm(out_ch), self.ac)
+        else:
+            self.fc = nn.Sequential(nn.Linear(in_ch, out_ch, bias=bias), self.ac)
+
+    def forward(self, x):
+        return self.fc(x)
+
+
+class transform_net(nn.Module):
+    """model_utils.py:60-89 (T-Net).  The 128->1024 layer + max over points runs fused."""
+
+    def __init__(self, in_ch, K=3):
+        super().__init__()
+        self.K = K
+        self.conv2d1 = conv_2d(in_ch, 64, 1)
+        self.conv2d2 = conv_2d(64, 128, 1)
+        self.conv2d3 = conv_2d(128, 1024, 1)
+        self.maxpool1 = nn.MaxPool2d(kernel_size=(512, 1))
+        self.fc1 = fc_layer(1024, 512)
+        self.fc2 = fc_layer(512, 256)
+        self.fc3 = nn.Linear(256, K * K)
+
+    def forward(self, x, DGCNN_Flag=False):
+        x = self.conv2d1(x)
+        x = self.conv2d2(x)
+        if DGCNN_Flag:
+            x = x.max(dim=-1, keepdim=False)[0]
+            x = torch.unsqueeze(x, dim=3)
+        if x.is_cuda:
+            x = self.conv2d3.pool_max(x.squeeze(3).transpose(1, 2))
+        else:
+            x = torch.max(self.conv2d3(x), dim=2, keepdim=False)[0]
+        x = x.view(x.size(0), -1)
+        x = self.fc3(self.fc2(self.fc1(x)))
+        iden = torch.eye(self.K, device=x.device, dtype=x.dtype).view(1, self.K * self.K)
+        return (x + iden).view(x.size(0), self.K, self.K)
+
+
+class adapt_layer_off(nn.Module):
+    """model_utils.py:92-128: self-adaptive nodes.  FPS / ball query / 64-NN grouping / 3-NN
+    interpolation indices come from one kernel launch each (no host syncs); the differentiable
+    gathers and the offset head stay on the autograd tape."""
+
+    def __init__(self, num_node=64, offset_dim=3, trans_dim_in=64, trans_dim_out=64, fc_dim=64):
+        super().__init__()
+        self.num_node = num_node
+        self.offset_dim = offset_dim
+        self.trans = conv_2d(trans_dim_in, trans_dim_out, 1)
+        self.pred_offset = nn.Sequential(nn.Conv2d(trans_dim_out, offset_dim, kernel_size=1, bias=False), nn.Tanh())
+        self.residual = conv_2d(trans_dim_in, fc_dim, 1)
+
+    def forward(self, input_fea, input_loc):
+        fea = input_fea.squeeze(3) if input_fea.dim() == 4 else input_fea  # [B,C,N]
+        fidx = point_utils.farthest_point_sample(input_loc, self.num_node)
+        f_loc = point_utils.index_points(input_loc, fidx)
+        f_fea = point_utils.index_points(fea, fidx)
+        gidx = point_utils.query_ball_point(0.3, 64, input_loc, f_loc)
+        g_fea = point_utils.index_points(fea, gidx) - f_fea.unsqueeze(3)
+        seman_trans = self.pred_offset(g_fea)
+        g_loc = point_utils.index_points(input_loc, gidx) - f_loc.unsqueeze(3)
+        node_offset = (seman_trans * g_loc).mean(dim=-1)
+        node_loc = f_loc + node_offset
+        gidx2 = point_utils.query_ball_point(None, 64, input_loc, node_loc)
+        residual_fea = self.residual(fea.unsqueeze(3)).squeeze(3)
+        node_fea, _ = torch.max(point_utils.index_points(residual_fea, gidx2), dim=-1, keepdim=True)
+        output_fea = point_utils.upsample_inter(input_loc, node_loc, fea, node_fea, k=3).unsqueeze(3)
+        return output_fea, node_fea, node_offset
+
+
+class focal_loss(nn.Module):
+    """model_utils.py:131-176, statefulness of ``alpha`` (re-gathered on every call, line 168)
+    included."""
+
+    def __init__(self, alpha=None, gamma=2, num_classes=3, size_average=True):
+        super().__init__()
+        self.size_average = size_average
+        if isinstance(alpha, list):
+            assert len(alpha) == num_classes
+            self.alpha = torch.Tensor(alpha)
+        else:
+            self.alpha = torch.Tensor([1 / num_classes] * num_classes)
+        self.gamma = gamma
+
+    def forward(self, preds, labels):
+        preds = preds.view(-1, preds.size(-1))
+        self.alpha = self.alpha.to(preds.device)
+        logsoft = F.log_softmax(preds, dim=1)
+        soft = torch.exp(logsoft).gather(1, labels.view(-1, 1))
+        logsoft = logsoft.gather(1, labels.view(-1, 1))
+        self.alpha = self.alpha.gather(0, labels.view(-1))
+        loss = -torch.mul(torch.pow((1 - soft), self.gamma), logsoft)
+        loss = torch.mul(self.alpha, loss.t())
+        return loss.mean() if self.size_average else loss.sum()
+
+
+def knn(x, k):
+    """model_utils.py:178-185.  x [B,C,N] -> int64 [B,N,k] (nearest first, self included).
+    Fused distance + top-k; the N x N matrix is never materialised."""
+    return ops.knn_cm(x, k).long()
+
+
+def get_graph_feature(x, k=20, idx=None):
+    """model_utils.py:188-210.  Returns the reference's [B,2C,N,k] edge tensor
+    ([x_j - x_i ; x_i]).  Kept for API parity; the encoders use ``conv_2d.edgeconv`` instead,
+    which never builds this tensor."""
+    B, N = x.size(0), x.size(2)
+    x = x.reshape(B, -1, N)
+    if idx is None:
+        idx = knn(x, k=k)
+    k = idx.shape[-1]
+    C = x.size(1)
+    xt = x.transpose(2, 1).contiguous()
+    flat = (idx.long() + torch.arange(B, device=x.device).view(-1, 1, 1) * N).view(-1)
+    feature = xt.view(B * N, C)[flat, :].view(B, N, k, C)
+    ctr = xt.view(B, N, 1, C).expand(B, N, k, C)
+    return torch.cat((feature - ctr, ctr), dim=3).permute(0, 3, 1, 2)

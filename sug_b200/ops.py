@@ -1,0 +1,361 @@
+"""Host-side operators over libsug_b200.so: torch tensors in, torch tensors out, autograd-aware.
+
+PyTorch is used only for device memory, the current stream and the autograd tape; all arithmetic
+of the hot path runs in the CUDA library through the C ABI (include/sug_b200.h).  Feature tensors
+are *point-major*: ``[B, N, C]`` with the channel stride 1, i.e. one row per point.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+_WS = {}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("sug_b200 operators run on CUDA tensors only (there is no CPU fallback)")
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def _rows(x: torch.Tensor, vec: bool = False) -> torch.Tensor:
+    """[B,N,C] view whose (b,n) rows have one uniform stride and unit channel stride
+    (``vec``: additionally 16-byte aligned rows for float4 access)."""
+    bad = x.stride(2) != 1 or x.stride(0) != x.shape[1] * x.stride(1) or x.dtype != torch.float32
+    if vec and not bad:
+        bad = x.stride(1) % 4 != 0 or x.data_ptr() % 16 != 0
+    if bad:
+        x = x.float().contiguous()
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# kNN
+# ------------------------------------------------------------------------------------------------
+def knn_cm(x: torch.Tensor, k: int) -> torch.Tensor:
+    """x [B,C,N] (reference layout, model_utils.py:178) -> int32 [B,N,k], nearest first."""
+    _need_cuda(x)
+    x = x.detach()
+    if x.dtype != torch.float32:
+        x = x.float()
+    B, C, N = x.shape
+    if x.stride(2) != 1:
+        x = x.contiguous()
+    idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sug_knn_f32(_ptr(x), B, C, N, k, x.stride(0), x.stride(2), x.stride(1), _ptr(idx), None, 0,
+                                   _stream()), "sug_knn_f32")
+    return idx
+
+
+def knn_pm(x: torch.Tensor, k: int) -> torch.Tensor:
+    """x [B,N,C] point-major -> int32 [B,N,k]."""
+    _need_cuda(x)
+    x = x.detach()
+    B, N, C = x.shape
+    if x.stride(2) != 1:
+        x = x.contiguous()
+    idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sug_knn_f32(_ptr(x), B, C, N, k, x.stride(0), x.stride(1), 1, _ptr(idx), None, 0, _stream()),
+                   "sug_knn_f32")
+    return idx
+
+
+def knn_reverse(idx: torch.Tensor):
+    B, N, k = idx.shape
+    rev_ptr = torch.empty(B, N + 1, dtype=torch.int32, device=idx.device)
+    rev_edge = torch.empty(B, N * k, dtype=torch.int32, device=idx.device)
+    lib = _lib.load()
+    with torch.cuda.device(idx.device):
+        _lib.check(lib.sug_knn_reverse(_ptr(idx), B, N, k, _ptr(rev_ptr), _ptr(rev_edge), _stream()),
+                   "sug_knn_reverse")
+    return rev_ptr, rev_edge
+
+
+# ------------------------------------------------------------------------------------------------
+# EdgeConv
+# ------------------------------------------------------------------------------------------------
+class _EdgeConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx, weight, gamma, beta, running_mean, running_var, training, eps, momentum, slope):
+        x = _rows(x)
+        B, N, C = x.shape
+        Cout = weight.shape[0]
+        k = idx.shape[2]
+        dev = x.device
+        w2 = weight.detach().reshape(Cout, 2 * C).contiguous()
+        P = B * N
+        out = torch.empty(B, N, Cout, dtype=torch.float32, device=dev)
+        ab = torch.empty(P, 2 * Cout, dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        ws = _workspace(lib.sug_edgeconv_ws_bytes(B, N, C, Cout, k), dev)
+        if training:
+            ext = torch.empty(P, Cout, dtype=torch.float32, device=dev)
+            ssum = torch.empty(P, Cout, dtype=torch.float32, device=dev)
+            arg = torch.empty(P, Cout, dtype=torch.uint8, device=dev)
+            save = torch.empty(2 * Cout, dtype=torch.float32, device=dev)
+        else:
+            ext = ssum = arg = save = None
+        with torch.cuda.device(dev):
+            _lib.check(lib.sug_edgeconv_fwd(_ptr(x), x.stride(1), _ptr(idx), _ptr(w2), _ptr(gamma.detach()),
+                                            _ptr(beta.detach()), _ptr(running_mean), _ptr(running_var), B, N, C, Cout,
+                                            k, eps, momentum, slope, int(training), _ptr(out), Cout, _ptr(ab),
+                                            _ptr(ext), _ptr(arg), _ptr(ssum), _ptr(save), _ptr(ws), ws.numel(),
+                                            _stream()), "sug_edgeconv_fwd")
+        if training:
+            ctx.save_for_backward(x, idx, w2, gamma, beta, ab, ext, arg, ssum, save)
+            ctx.slope = slope
+            ctx.wshape = weight.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, idx, w2, gamma, beta, ab, ext, arg, ssum, save = ctx.saved_tensors
+        B, N, C = x.shape
+        Cout = w2.shape[0]
+        k = idx.shape[2]
+        dev = x.device
+        gout = _rows(gout, vec=True)
+        lib = _lib.load()
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty(B, N, C, dtype=torch.float32, device=dev) if need_dx else None
+        dw = torch.empty(Cout, 2 * C, dtype=torch.float32, device=dev)
+        dgamma = torch.empty(Cout, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(Cout, dtype=torch.float32, device=dev)
+        dab = torch.empty(B * N, 2 * Cout, dtype=torch.float32, device=dev)
+        ws = _workspace(lib.sug_edgeconv_ws_bytes(B, N, C, Cout, k), dev)
+        with torch.cuda.device(dev):
+            rev_ptr, rev_edge = knn_reverse(idx)
+            _lib.check(lib.sug_edgeconv_bwd(_ptr(gout), gout.stride(1), _ptr(x), x.stride(1), _ptr(idx),
+                                            _ptr(rev_ptr), _ptr(rev_edge), _ptr(w2), _ptr(gamma.detach()),
+                                            _ptr(beta.detach()), _ptr(ab), _ptr(ext), _ptr(arg), _ptr(ssum),
+                                            _ptr(save), B, N, C, Cout, k, ctx.slope, _ptr(dx), C, 0, _ptr(dw),
+                                            _ptr(dgamma), _ptr(dbeta), _ptr(dab), _ptr(ws), ws.numel(), _stream()),
+                       "sug_edgeconv_bwd")
+        return dx, None, dw.view(ctx.wshape), dgamma, dbeta, None, None, None, None, None, None
+
+
+def edgeconv(x, idx, weight, gamma, beta, running_mean, running_var, training: bool, eps: float = 1e-5,
+             momentum: float = 0.1, slope: float = 0.01):
+    """Fused get_graph_feature -> 1x1 conv -> BatchNorm2d -> LeakyReLU -> max over k.
+    x [B,N,C] point-major, idx int32 [B,N,k], weight [Cout,2C,1,1] -> [B,N,Cout]."""
+    _need_cuda(x, idx, weight)
+    return _EdgeConvFn.apply(x, idx, weight, gamma, beta, running_mean, running_var, bool(training), float(eps),
+                             float(momentum), float(slope))
+
+
+# ------------------------------------------------------------------------------------------------
+# shared MLP + BN + act + global pool
+# ------------------------------------------------------------------------------------------------
+POOL_MAX, POOL_MAX_AVG = 0, 1
+
+
+class _MlpPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, eps, momentum, slope, pool):
+        x = _rows(x)
+        B, N, Cin = x.shape
+        Cout = weight.shape[0]
+        dev = x.device
+        w2 = weight.detach().reshape(Cout, Cin).contiguous()
+        y = torch.empty(B * N, Cout, dtype=torch.float32, device=dev)
+        out = torch.empty(B, Cout * (2 if pool == POOL_MAX_AVG else 1), dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        ws = _workspace(lib.sug_mlp_pool_ws_bytes(B, N, Cin, Cout), dev)
+        argext = torch.empty(B, Cout, dtype=torch.int32, device=dev) if training else None
+        save = torch.empty(2 * Cout, dtype=torch.float32, device=dev) if training else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.sug_mlp_pool_fwd(_ptr(x), x.stride(1), _ptr(w2), _ptr(None if bias is None else bias.detach()),
+                                            _ptr(gamma.detach()), _ptr(beta.detach()), _ptr(running_mean),
+                                            _ptr(running_var), B, N, Cin, Cout, eps, momentum, slope, pool,
+                                            int(training), _ptr(y), _ptr(out), _ptr(argext), _ptr(save), _ptr(ws),
+                                            ws.numel(), _stream()), "sug_mlp_pool_fwd")
+        if training:
+            ctx.save_for_backward(x, w2, gamma, beta, y, argext, save)
+            ctx.meta = (slope, pool, weight.shape, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w2, gamma, beta, y, argext, save = ctx.saved_tensors
+        slope, pool, wshape, has_bias = ctx.meta
+        B, N, Cin = x.shape
+        Cout = w2.shape[0]
+        dev = x.device
+        gout = gout.contiguous()
+        lib = _lib.load()
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty(B, N, Cin, dtype=torch.float32, device=dev) if need_dx else None
+        dw = torch.empty(Cout, Cin, dtype=torch.float32, device=dev)
+        dbias = torch.empty(Cout, dtype=torch.float32, device=dev) if has_bias else None
+        dgamma = torch.empty(Cout, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(Cout, dtype=torch.float32, device=dev)
+        ws = _workspace(lib.sug_mlp_pool_ws_bytes(B, N, Cin, Cout), dev)
+        with torch.cuda.device(dev):
+            # y is consumed (overwritten with dL/dy): the tape is single-use, like any freed buffer
+            _lib.check(lib.sug_mlp_pool_bwd(_ptr(gout), _ptr(x), x.stride(1), _ptr(w2), None, _ptr(gamma.detach()),
+                                            _ptr(beta.detach()), _ptr(y), _ptr(argext), _ptr(save), B, N, Cin, Cout,
+                                            slope, pool, _ptr(dx), Cin, 0, _ptr(dw), _ptr(dbias), _ptr(dgamma),
+                                            _ptr(dbeta), _ptr(ws), ws.numel(), _stream()), "sug_mlp_pool_bwd")
+        return dx, dw.view(wshape), dbias, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def mlp_bn_act_pool(x, weight, bias, gamma, beta, running_mean, running_var, training: bool, slope: float,
+                    pool: int, eps: float = 1e-5, momentum: float = 0.1):
+    """x [B,N,Cin] -> [B,Cout] (max) or [B,2*Cout] (max || avg) of act(BN(x W^T + bias))."""
+    _need_cuda(x, weight)
+    return _MlpPoolFn.apply(x, weight, bias, gamma, beta, running_mean, running_var, bool(training), float(eps),
+                            float(momentum), float(slope), int(pool))
+
+
+# ------------------------------------------------------------------------------------------------
+# MMD + Chamfer
+# ------------------------------------------------------------------------------------------------
+class _MmdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, Y, weights, sigmas, biased):
+        m, D = X.shape
+        dev = X.device
+        z = torch.cat((X.detach(), Y.detach()), 0).float().contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        coef = torch.empty(2 * m, 2 * m, dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        ws = _workspace(lib.sug_mmd_ws_bytes(m, D), dev)
+        sg = (ctypes.c_float * len(sigmas))(*[float(s) for s in sigmas])
+        w = None
+        if weights is not None:
+            w = weights.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+            if w.numel() != m:
+                raise RuntimeError(f"sample_weights has {w.numel()} entries, expected {m}")
+        with torch.cuda.device(dev):
+            _lib.check(lib.sug_mmd_rbf_fwd(_ptr(z), D, m, D, ctypes.cast(sg, ctypes.c_void_p), len(sigmas), _ptr(w),
+                                           int(biased), _ptr(loss), _ptr(coef), _ptr(ws), ws.numel(), _stream()),
+                       "sug_mmd_rbf_fwd")
+        ctx.save_for_backward(z, coef)
+        ctx.m = m
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        z, coef = ctx.saved_tensors
+        m = ctx.m
+        D = z.shape[1]
+        dz = torch.empty_like(z)
+        g = gloss.detach().float().contiguous()
+        lib = _lib.load()
+        with torch.cuda.device(z.device):
+            _lib.check(lib.sug_mmd_rbf_bwd(_ptr(z), D, m, D, _ptr(coef), _ptr(g), _ptr(dz), D, _stream()),
+                       "sug_mmd_rbf_bwd")
+        return dz[:m], dz[m:], None, None, None
+
+
+def mix_rbf_mmd2(X, Y, sigma_list: Sequence[float], biased: bool = True, sample_weights=None):
+    _need_cuda(X, Y)
+    if X.shape != Y.shape:
+        raise AssertionError("X and Y must have the same shape")  # mmd.py:240
+    return _MmdFn.apply(X, Y, sample_weights, tuple(sigma_list), bool(biased))
+
+
+def chamfer(p1: torch.Tensor, p2: torch.Tensor):
+    """p1 [B,N,3], p2 [B,M,3] -> (dist1 [B,N], dist2 [B,M]) squared NN distances."""
+    _need_cuda(p1, p2)
+    p1 = p1.detach().float().contiguous()
+    p2 = p2.detach().float().contiguous()
+    B, N, _ = p1.shape
+    M = p2.shape[1]
+    d1 = torch.empty(B, N, dtype=torch.float32, device=p1.device)
+    d2 = torch.empty(B, M, dtype=torch.float32, device=p1.device)
+    lib = _lib.load()
+    with torch.cuda.device(p1.device):
+        _lib.check(lib.sug_chamfer_f32(_ptr(p1), _ptr(p2), B, N, M, _ptr(d1), _ptr(d2), _stream()), "sug_chamfer_f32")
+    return d1, d2
+
+
+# ------------------------------------------------------------------------------------------------
+# index builders of the self-adaptive node layer (all take the reference's [B,3,N] layout)
+# ------------------------------------------------------------------------------------------------
+def _xyz(t):
+    _need_cuda(t)
+    return t.detach().float().contiguous()
+
+
+def fps(xyz: torch.Tensor, npoint: int, start: torch.Tensor) -> torch.Tensor:
+    xyz = _xyz(xyz)
+    B, _, N = xyz.shape
+    st = start.to(device=xyz.device, dtype=torch.int32).contiguous()
+    out = torch.empty(B, npoint, dtype=torch.int32, device=xyz.device)
+    lib = _lib.load()
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.sug_fps(_ptr(xyz), B, N, npoint, _ptr(st), _ptr(out), _stream()), "sug_fps")
+    return out
+
+
+def ball_query(xyz, query, radius: float, nsample: int) -> torch.Tensor:
+    xyz, query = _xyz(xyz), _xyz(query)
+    B, _, N = xyz.shape
+    S = query.shape[2]
+    out = torch.empty(B, S, nsample, dtype=torch.int32, device=xyz.device)
+    lib = _lib.load()
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.sug_ball_query(_ptr(xyz), _ptr(query), B, N, S, float(radius), nsample, _ptr(out), _stream()),
+                   "sug_ball_query")
+    return out
+
+
+def knn_query(xyz, query, nsample: int) -> torch.Tensor:
+    xyz, query = _xyz(xyz), _xyz(query)
+    B, _, N = xyz.shape
+    S = query.shape[2]
+    out = torch.empty(B, S, nsample, dtype=torch.int32, device=xyz.device)
+    lib = _lib.load()
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.sug_knn_query(_ptr(xyz), _ptr(query), B, N, S, nsample, _ptr(out), _stream()), "sug_knn_query")
+    return out
+
+
+def three_nn(xyz, nodes, k: int = 3) -> torch.Tensor:
+    xyz, nodes = _xyz(xyz), _xyz(nodes)
+    B, _, N = xyz.shape
+    M = nodes.shape[2]
+    out = torch.empty(B, N, k, dtype=torch.int32, device=xyz.device)
+    lib = _lib.load()
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.sug_three_nn(_ptr(xyz), _ptr(nodes), B, N, M, k, _ptr(out), _stream()), "sug_three_nn")
+    return out
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a [M,K] (any strides) x b [N,K]^T -> [M,N]; the library's fp32 GEMM, exposed for tests."""
+    _need_cuda(a, b)
+    M, K = a.shape
+    N = b.shape[0]
+    c = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        _lib.check(lib.sug_gemm_f32(_ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), _ptr(bias),
+                                    _ptr(c), N, M, N, K, 0, _stream()), "sug_gemm_f32")
+    return c

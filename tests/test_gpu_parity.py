@@ -1,0 +1,461 @@
+"""Parity of the sm_100a kernels (through the C ABI) against the CPU oracle and the fixtures that
+were generated from the reference.  Tolerances (BASELINE.json north_star): neighbour sets
+bit-exact except near-ties with relative gap < 1e-6 (counted and reported); outputs, losses and
+gradients within rel 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sug_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def S():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import sug_b200  # noqa: F401
+    from sug_b200 import Model, mmd, model_pointnet, model_utils, ops, point_utils, step
+    import types
+    return types.SimpleNamespace(Model=Model, mmd=mmd, model_pointnet=model_pointnet, model_utils=model_utils,
+                                 ops=ops, point_utils=point_utils, step=step)
+
+
+def feat_input(B, C, N, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return torch.from_numpy(rng.standard_normal((B, C, N)).astype(np.float32))
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def assert_close(a, b, tol=1e-3, what=""):
+    e = relerr(a, b)
+    assert e <= tol, f"{what}: relative error {e:.3e} > {tol}"
+
+
+def knn_report(x_cpu, idx_ours, k):
+    """Compare neighbour sets with torch.topk on the reference fp32 distance matrix.
+    Returns (rows_differing, worst gap relative to |d_k|, worst gap relative to |xi|^2+|xj|^2)."""
+    D = O.pairwise_neg_sqdist(x_cpu)  # [B,N,N]
+    B, N, _ = D.shape
+    top = D.topk(k + 1 if N > k else k, dim=-1)
+    ref = top[1][..., :k]
+    ours = idx_ours.cpu().long()
+    assert ours.min() >= 0 and ours.max() < N
+    # no duplicates in a row
+    so = ours.sort(dim=-1)[0]
+    assert bool((so[..., 1:] != so[..., :-1]).all()), "duplicate neighbour in a row"
+    sr = ref.sort(dim=-1)[0]
+    diff_rows = (so != sr).any(-1)
+    n_diff = int(diff_rows.sum())
+    worst_d, worst_n = 0.0, 0.0
+    if n_diff:
+        dk = top[0][..., k - 1]  # k-th best key of the oracle
+        xx = (x_cpu ** 2).sum(1)  # [B,N]
+        for b, r in diff_rows.nonzero().tolist():
+            mine = set(ours[b, r].tolist())
+            theirs = set(ref[b, r].tolist())
+            for j in mine - theirs:
+                gap = abs(float(D[b, r, j] - dk[b, r]))
+                worst_d = max(worst_d, gap / max(abs(float(dk[b, r])), 1e-30))
+                worst_n = max(worst_n, gap / float(xx[b, r] + xx[b, j] + 1e-30))
+    # ordering: keys along our list must be non-increasing up to fp32 noise
+    keys = torch.gather(D, 2, ours)
+    xx = (x_cpu ** 2).sum(1)
+    scale = (xx.unsqueeze(-1) + torch.gather(xx.unsqueeze(1).expand(B, N, N), 2, ours))
+    assert bool(((keys[..., 1:] - keys[..., :-1]) <= 2e-6 * scale[..., 1:] + 1e-12).all()), "list not sorted nearest-first"
+    return n_diff, worst_d, worst_n
+
+
+# ------------------------------------------------------------------------------------------------
+def test_gemm(S):
+    torch.manual_seed(0)
+    for (M, N, K) in [(300, 70, 3), (257, 129, 64), (1024, 128, 6), (128, 128, 4106)]:
+        a = torch.randn(M, K, device=DEV)
+        b = torch.randn(N, K, device=DEV)
+        ref = (a.double() @ b.double().t())
+        assert_close(S.ops.gemm(a, b), ref, 2e-6, f"gemm NT {M}x{N}x{K}")
+    # transposed operands + split-K (weight-gradient shape)
+    P, Co, C = 20000, 96, 40
+    dy = torch.randn(P, Co, device=DEV)
+    x = torch.randn(P, C, device=DEV)
+    ref = dy.double().t() @ x.double()
+    assert_close(S.ops.gemm(dy.t(), x.t()), ref, 5e-6, "gemm TN split-K")
+    w = torch.randn(Co, C, device=DEV)
+    assert_close(S.ops.gemm(dy, w.t()), dy.double() @ w.double(), 2e-6, "gemm NN")
+    bias = torch.randn(N, device=DEV)
+    assert_close(S.ops.gemm(a, b, bias), a.double() @ b.double().t() + bias.double(), 2e-6, "gemm bias")
+
+
+@pytest.mark.parametrize("C,N", [(3, 256), (64, 256), (128, 128)])
+def test_knn_golden(S, golden, C, N):
+    x = O.synth_clouds(2, N, 10 + C)[0].squeeze(-1) if C == 3 else feat_input(2, C, N, 10 + C)
+    idx = S.model_utils.knn(x.to(DEV), 20)
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (2, N, 20)
+    g = torch.from_numpy(golden(f"knn_c{C}")["idx"].astype(np.int64))
+    same = (idx.cpu().sort(-1)[0] == g.sort(-1)[0]).all(-1)
+    n_diff, wd, wn = knn_report(x, idx, 20)
+    print(f"knn golden C={C}: rows differing from reference {int((~same).sum())}, near-tie gap {wd:.2e}/{wn:.2e}")
+    assert wn < 1e-6
+    assert int((~same).sum()) <= max(1, int(2e-3 * same.numel()))
+
+
+@pytest.mark.parametrize("B,C,N,k,layout", [(4, 3, 1024, 20, "cm"), (4, 64, 1024, 20, "pm"), (2, 128, 1024, 40, "pm"),
+                                            (3, 3, 1000, 20, "cm"), (2, 64, 333, 20, "pm"), (1, 7, 50, 50, "cm")])
+def test_knn_oracle(S, B, C, N, k, layout):
+    x = O.synth_clouds(B, N, 3)[0].squeeze(-1) if C == 3 else feat_input(B, C, N, 5)
+    if layout == "cm":
+        idx = S.ops.knn_cm(x.to(DEV), k)
+    else:
+        idx = S.ops.knn_pm(x.to(DEV).transpose(1, 2).contiguous(), k)
+    n_diff, wd, wn = knn_report(x, idx, k)
+    print(f"knn B={B} C={C} N={N} k={k}: {n_diff}/{B * N} rows differ (near-ties), worst gap rel d_k {wd:.2e}, "
+          f"rel norms {wn:.2e}")
+    assert wn < 1e-6, "a neighbour differs from torch.topk beyond an fp32 near-tie"
+    assert n_diff <= max(2, int(2e-3 * B * N))
+    if N >= k and C == 3:
+        assert bool((idx[..., 0].cpu() == torch.arange(N).view(1, N)).all()), "self must be neighbour 0"
+
+
+def test_knn_reverse(S):
+    x = feat_input(3, 16, 200, 9)
+    idx = S.ops.knn_pm(x.to(DEV).transpose(1, 2).contiguous(), 20)
+    rp, re = S.ops.knn_reverse(idx)
+    idx_c, rp, re = idx.cpu().numpy(), rp.cpu().numpy(), re.cpu().numpy()
+    for b in range(3):
+        assert rp[b, 0] == 0 and rp[b, -1] == 200 * 20
+        exp = {j: [] for j in range(200)}
+        for i in range(200):
+            for s in range(20):
+                exp[idx_c[b, i, s]].append((i << 8) | s)
+        for j in range(200):
+            got = re[b, rp[b, j]:rp[b, j + 1]].tolist()
+            assert got == sorted(exp[j]), (b, j)
+
+
+def _edge_case(S, B, C, N, Co, k, seed, golden_dict=None):
+    x = feat_input(B, C, N, seed)
+    rng = np.random.Generator(np.random.PCG64(seed + 1))
+    W = torch.from_numpy(rng.standard_normal((Co, 2 * C, 1, 1)).astype(np.float32) * 0.3)
+    ga = rng.uniform(0.5, 1.5, Co).astype(np.float32)
+    ga[::3] *= -1
+    be = torch.from_numpy(rng.standard_normal(Co).astype(np.float32) * 0.1)
+    Rw = torch.from_numpy(rng.standard_normal((B, Co, N)).astype(np.float32))
+    # oracle
+    xo = x.clone().requires_grad_(True)
+    sd = {"b.conv.0.weight": W.clone().requires_grad_(True), "b.conv.1.weight": torch.from_numpy(ga).clone().requires_grad_(True),
+          "b.conv.1.bias": be.clone().requires_grad_(True), "b.conv.1.running_mean": torch.zeros(Co),
+          "b.conv.1.running_var": torch.ones(Co), "b.conv.1.num_batches_tracked": torch.zeros((), dtype=torch.int64)}
+    idx = O.knn(x, k)
+    out_o = O.edgeconv(xo, sd, "b", True, k=k, idx=idx)
+    (out_o * Rw).sum().backward()
+    # ours
+    blk = S.model_utils.conv_2d(2 * C, Co, 1, activation="leakyrelu", bias=False).to(DEV)
+    with torch.no_grad():
+        blk.conv[0].weight.copy_(W)
+        blk.conv[1].weight.copy_(torch.from_numpy(ga))
+        blk.conv[1].bias.copy_(be)
+    blk.train()
+    xg = x.to(DEV).transpose(1, 2).contiguous().requires_grad_(True)
+    out = blk.edgeconv(xg, idx.to(DEV).int())
+    (out * Rw.to(DEV).transpose(1, 2)).sum().backward()
+    assert_close(out.transpose(1, 2), out_o, 1e-4, "edgeconv out")
+    assert_close(xg.grad.transpose(1, 2), xo.grad, 1e-3, "edgeconv dx")
+    assert_close(blk.conv[0].weight.grad, sd["b.conv.0.weight"].grad, 1e-3, "edgeconv dW")
+    assert_close(blk.conv[1].weight.grad, sd["b.conv.1.weight"].grad, 1e-3, "edgeconv dgamma")
+    assert_close(blk.conv[1].bias.grad, sd["b.conv.1.bias"].grad, 1e-3, "edgeconv dbeta")
+    assert_close(blk.conv[1].running_mean, sd["b.conv.1.running_mean"], 1e-4, "running_mean")
+    assert_close(blk.conv[1].running_var, sd["b.conv.1.running_var"], 1e-4, "running_var")
+    assert int(blk.conv[1].num_batches_tracked) == 1
+    if golden_dict is not None:
+        assert_close(out.transpose(1, 2), golden_dict["out"], 1e-4, "edgeconv out vs reference fixture")
+        assert_close(xg.grad.transpose(1, 2), golden_dict["dx"], 1e-3, "edgeconv dx vs fixture")
+        assert_close(blk.conv[0].weight.grad, golden_dict["dW"], 1e-3, "edgeconv dW vs fixture")
+        assert_close(blk.conv[1].weight.grad, golden_dict["dgamma"], 1e-3, "dgamma vs fixture")
+        assert_close(blk.conv[1].running_var, golden_dict["running_var"], 1e-4, "running_var vs fixture")
+    # eval mode uses the running statistics
+    blk.eval()
+    sd_eval = {k_: v.detach() for k_, v in sd.items()}
+    with torch.no_grad():
+        out_e = blk.edgeconv(xg.detach(), idx.to(DEV).int())
+        out_eo = O.edgeconv(x, sd_eval, "b", False, k=k, idx=idx)
+    assert_close(out_e.transpose(1, 2), out_eo, 1e-4, "edgeconv eval")
+
+
+def test_edgeconv_golden(S, golden):
+    _edge_case(S, 2, 8, 128, 16, 20, 21, golden("edgeconv_block"))
+
+
+@pytest.mark.parametrize("B,C,N,Co,k", [(2, 3, 512, 64, 20), (2, 64, 1024, 64, 20), (2, 64, 256, 128, 40),
+                                        (1, 128, 300, 256, 20)])
+def test_edgeconv_oracle(S, B, C, N, Co, k):
+    _edge_case(S, B, C, N, Co, k, 100 + C + Co)
+
+
+@pytest.mark.parametrize("pool,slope,bias", [(1, 0.2, False), (0, 0.0, True)])
+def test_mlp_pool(S, pool, slope, bias):
+    import torch.nn.functional as F
+    B, N, Ci, Co = 3, 500, 72, 136
+    rng = np.random.Generator(np.random.PCG64(77))
+    x = torch.from_numpy(rng.standard_normal((B, N, Ci)).astype(np.float32))
+    W = torch.from_numpy(rng.standard_normal((Co, Ci)).astype(np.float32) * 0.2)
+    bi = torch.from_numpy(rng.standard_normal(Co).astype(np.float32)) if bias else None
+    ga = rng.uniform(0.5, 1.5, Co).astype(np.float32)
+    ga[::4] *= -1
+    ga = torch.from_numpy(ga)
+    be = torch.from_numpy(rng.standard_normal(Co).astype(np.float32) * 0.1)
+    Rw = torch.from_numpy(rng.standard_normal((B, Co * (2 if pool else 1))).astype(np.float32))
+    # oracle: conv1d -> BN -> act -> pool
+    ps = [t.clone().requires_grad_(True) for t in (x, W, ga, be)] + ([bi.clone().requires_grad_(True)] if bias else [None])
+    rm, rv = torch.zeros(Co), torch.ones(Co)
+    y = F.conv1d(ps[0].transpose(1, 2), ps[1].unsqueeze(-1), ps[4])
+    z = F.leaky_relu(F.batch_norm(y, rm, rv, ps[2], ps[3], True, 0.1, 1e-5), slope)
+    o_ref = torch.cat((z.max(2)[0], z.mean(2)), 1) if pool else z.max(2)[0]
+    (o_ref * Rw).sum().backward()
+    # ours
+    gs = [t.to(DEV).requires_grad_(True) for t in (x, W, ga, be)] + ([bi.to(DEV).requires_grad_(True)] if bias else [None])
+    rmg, rvg = torch.zeros(Co, device=DEV), torch.ones(Co, device=DEV)
+    o = S.ops.mlp_bn_act_pool(gs[0], gs[1], gs[4], gs[2], gs[3], rmg, rvg, True, slope, pool)
+    (o * Rw.to(DEV)).sum().backward()
+    assert_close(o, o_ref, 1e-4, "pool out")
+    for a, b, n in zip(gs[:4], ps[:4], ("dx", "dW", "dgamma", "dbeta")):
+        assert_close(a.grad, b.grad, 1e-3, "pool " + n)
+    if bias:
+        assert float(gs[4].grad.abs().max()) <= 1e-6 + 1e-3 * float(ps[4].grad.abs().max() + 1e-6)
+    assert_close(rmg, rm, 1e-4, "pool running_mean")
+    assert_close(rvg, rv, 1e-4, "pool running_var")
+    with torch.no_grad():
+        oe = S.ops.mlp_bn_act_pool(gs[0], gs[1], gs[4], gs[2], gs[3], rmg, rvg, False, slope, pool)
+        ze = F.leaky_relu(F.batch_norm(F.conv1d(x.transpose(1, 2), W.unsqueeze(-1), bi), rm, rv, ga, be, False, 0.1, 1e-5), slope)
+        oe_ref = torch.cat((ze.max(2)[0], ze.mean(2)), 1) if pool else ze.max(2)[0]
+    assert_close(oe, oe_ref, 1e-4, "pool eval")
+
+
+def _mmd_inputs():
+    rng = np.random.Generator(np.random.PCG64(51))
+    m = 16
+    t = lambda a: torch.from_numpy(np.asarray(a))
+    X = t(rng.standard_normal((m, 4096)).astype(np.float32))
+    Y = t((rng.standard_normal((m, 4096)) * 1.1 + 0.1).astype(np.float32))
+    Xs = t(rng.standard_normal((m, 256)).astype(np.float32) * 0.5)
+    Ys = t(rng.standard_normal((m, 256)).astype(np.float32) * 0.6)
+    ls = t(rng.integers(0, 10, m).astype(np.int64))
+    lt = t(rng.integers(0, 10, m).astype(np.int64))
+    w = t(rng.uniform(0, 2, (1, m)).astype(np.float32))
+    ps = t(rng.standard_normal((m, 10)).astype(np.float32))
+    pt = t(rng.standard_normal((m, 10)).astype(np.float32))
+    ds, dt = O.synth_clouds(m, 256, 52)[0], O.synth_clouds(m, 256, 53)[0]
+    return X, Y, Xs, Ys, ls, lt, w, ps, pt, ds, dt
+
+
+def test_mmd_golden(S, golden):
+    g = golden("mmd")
+    X, Y, Xs, Ys, ls, lt, w, ps, pt, ds, dt = _mmd_inputs()
+    d = lambda t: t.to(DEV)
+    Xg, Yg = d(X).requires_grad_(True), d(Y).requires_grad_(True)
+    assert_close(S.mmd.mix_rbf_mmd2(Xg, Yg, S.mmd.sigma_list), g["v_plain"], 1e-4, "mmd plain")
+    v = S.mmd.mix_rbf_mmd2(Xg, Yg, S.mmd.sigma_list, sample_weights=d(w))
+    v.backward()
+    assert_close(v, g["v_w"], 1e-4, "mmd weighted")
+    assert_close(Xg.grad, g["dX"], 1e-3, "mmd dX")
+    assert_close(Yg.grad, g["dY"], 1e-3, "mmd dY")
+    Xsg, Ysg = d(Xs).requires_grad_(True), d(Ys).requires_grad_(True)
+    v = S.mmd.mix_rbf_mmd2(Xsg, Ysg, S.mmd.sigma_list, sample_weights=d(w))
+    (3.0 * v).backward()
+    assert_close(v, g["v_sem"], 1e-4, "mmd sem")
+    assert_close(Xsg.grad, 3.0 * g["dXs"], 1e-3, "mmd dXs")
+    assert_close(Ysg.grad, 3.0 * g["dYs"], 1e-3, "mmd dYs")
+    assert_close(S.mmd.geometric_weights(d(ds), d(dt), weighting="mean2one"), g["geo_w"], 1e-4, "geo weights")
+    assert_close(S.mmd.prob_weights_soft(d(ps), d(pt), d(ls), d(lt), 0.5, "mean2one"), g["sem_w"], 1e-3, "sem weights")
+    assert_close(S.mmd.mmd_cal(d(ls), d(X), d(lt), d(Y), O.SUG_CFG["GEO_MMD"], data_s=d(ds), data_t=d(dt)), g["geo"],
+                 1e-4, "mmd_cal geo")
+    assert_close(S.mmd.mmd_cal(d(ls), d(Xs), d(lt), d(Ys), O.SUG_CFG["SEM_MMD"], data_s=d(ps), data_t=d(pt)), g["sem"],
+                 1e-3, "mmd_cal sem")
+    c1, c2 = S.ops.chamfer(d(ds).squeeze(-1).transpose(1, 2), d(dt).squeeze(-1).transpose(1, 2))
+    assert_close(c1, g["cd1"], 1e-5, "chamfer d1")
+    assert_close(c2, g["cd2"], 1e-5, "chamfer d2")
+
+
+def test_mmd_unbiased_and_sizes(S):
+    rng = np.random.Generator(np.random.PCG64(5))
+    for m, D in ((64, 4106), (64, 266), (7, 33)):
+        X = torch.from_numpy(rng.standard_normal((m, D)).astype(np.float32) * 0.3)
+        Y = torch.from_numpy(rng.standard_normal((m, D)).astype(np.float32) * 0.35)
+        for biased in (True, False):
+            Xo, Yo = X.clone().requires_grad_(True), Y.clone().requires_grad_(True)
+            vo = O.mix_rbf_mmd2(Xo, Yo, biased=biased)
+            vo.backward()
+            Xg, Yg = X.to(DEV).requires_grad_(True), Y.to(DEV).requires_grad_(True)
+            vg = S.mmd.mix_rbf_mmd2(Xg, Yg, S.mmd.sigma_list, biased=biased)
+            vg.backward()
+            assert_close(vg, vo, 1e-4, f"mmd m={m} D={D} biased={biased}")
+            assert_close(Xg.grad, Xo.grad, 2e-3, "mmd dX")
+            assert_close(Yg.grad, Yo.grad, 2e-3, "mmd dY")
+
+
+def test_adapt_indices(S):
+    B, N = 3, 1024
+    loc = O.synth_clouds(B, N, 61)[0].squeeze(-1)
+    start = torch.tensor([5, 1000, 333])
+    f_o = O.farthest_point_sample(loc, 64, start)
+    f_g = S.ops.fps(loc.to(DEV), 64, start).cpu().long()
+    assert bool((f_o == f_g).all()), "FPS indices differ"
+    f_loc = O.index_points(loc, f_o)
+    b_o = O.query_ball_point(0.3, 64, loc, f_loc)
+    b_g = S.ops.ball_query(loc.to(DEV), f_loc.to(DEV), 0.3, 64).cpu().long()
+    frac = float((b_o != b_g).float().mean())
+    print(f"ball query: fraction of differing entries {frac:.2e}")
+    assert frac < 1e-3
+    node = f_loc + 0.01 * feat_input(B, 3, 64, 62)
+    k_o = O.query_ball_point(None, 64, loc, node)
+    k_g = S.ops.knn_query(loc.to(DEV), node.to(DEV), 64).cpu().long()
+    same = (k_o.sort(-1)[0] == k_g.sort(-1)[0]).all(-1).float().mean()
+    assert float(same) > 0.995, f"64-NN sets agree on only {float(same):.4f} of the nodes"
+    d, i3 = O.square_distance(loc, node).sort(dim=-1)
+    t_g = S.ops.three_nn(loc.to(DEV), node.to(DEV), 3).cpu().long()
+    assert float((i3[..., :3] == t_g).float().mean()) > 0.999
+
+
+def test_adapt_layer_golden(S, golden):
+    g = golden("adapt_layer")
+    sd = O.synth_state("Net_MDA:DGCNN")
+    ad = S.model_utils.adapt_layer_off()
+    ad.load_state_dict({k[len("g.node_fea_adapt."):]: v for k, v in sd.items() if k.startswith("g.node_fea_adapt.")})
+    ad = ad.to(DEV).train()
+    loc = O.synth_clouds(2, 256, 31)[0].squeeze(-1)
+    fea = feat_input(2, 64, 256, 32)
+    torch.manual_seed(5)
+    o, nf, no = ad(fea.unsqueeze(3).to(DEV), loc.to(DEV))
+    assert_close(o, g["out"], 1e-3, "adapt out")
+    assert_close(nf, g["node_fea"], 1e-3, "adapt node_fea")
+    assert_close(no, g["node_off"], 1e-3, "adapt node_off")
+
+
+def _load(mod, spec, seed=666):
+    mod.load_state_dict(O.synth_state(spec, seed), strict=True)
+    return mod.to(DEV)
+
+
+def test_dgcnn_g_golden(S, golden):
+    g = golden("dgcnn_g")
+    x, _ = O.synth_clouds(2, 1024, 41)
+    net = _load(S.Model.Net_MDA("DGCNN"), "Net_MDA:DGCNN").train()
+    torch.manual_seed(7)
+    f, n, _ = net.g(x.to(DEV), node=True)
+    assert_close(f, g["feat_train"], 1e-3, "DGCNN feat (train)")
+    assert_close(n, g["node_train"], 1e-3, "DGCNN node_fea (train)")
+    net.eval()
+    torch.manual_seed(8)
+    with torch.no_grad():
+        f, n, _ = net.g(x.to(DEV), node=True)
+    assert_close(f, g["feat_eval"], 1e-3, "DGCNN feat (eval)")
+    assert_close(n, g["node_eval"], 1e-3, "DGCNN node_fea (eval)")
+    assert_close(net.g.conv1.conv[1].running_mean, g["rm1"], 1e-4, "rm1")
+    assert_close(net.g.conv4.conv[1].running_var, g["rv4"], 1e-3, "rv4")
+    assert_close(net.g.bn5.running_mean, g["rm5"], 1e-3, "rm5")
+    assert_close(net.g.bn5.running_var, g["rv5"], 1e-3, "rv5")
+    assert int(net.g.bn5.num_batches_tracked) == 1 and int(net.g.conv3.conv[1].num_batches_tracked) == 1
+
+
+def test_net_mda_golden(S, golden):
+    g = golden("net_mda_dgcnn")
+    x, _ = O.synth_clouds(2, 1024, 41)
+    net = _load(S.Model.Net_MDA("DGCNN"), "Net_MDA:DGCNN").train()
+    for hd in (net.c1, net.c2):  # CPU and CUDA dropout streams differ: compare with dropout off
+        hd.dropout1.p = hd.dropout2.p = 0.0
+    sd = O.synth_state("Net_MDA:DGCNN")
+    torch.manual_seed(11)
+    y1, y2, s1, s2 = net(x.to(DEV), semantic_adaption=True)
+    torch.manual_seed(11)
+    o1, o2, t1, t2 = O.net_mda(x, sd, True, semantic_adaption=True, drop_p=0.0)
+    for a, b, n in ((y1, o1, "y1"), (y2, o2, "y2"), (s1, t1, "s1"), (s2, t2, "s2")):
+        assert_close(a, b, 1e-3, n)
+    torch.manual_seed(12)
+    ns = net(x.to(DEV), node_adaptation_s=True)
+    assert_close(ns, g["node_s"], 2e-3, "node_s vs fixture")
+    torch.manual_seed(13)
+    nt = net(x.to(DEV), node_adaptation_t=True)
+    assert_close(nt, g["node_t"], 2e-3, "node_t vs fixture")
+
+
+def test_dgcnn_cls_golden(S, golden):
+    x, _ = O.synth_clouds(2, 1024, 41)
+    cls = _load(S.model_pointnet.DGCNN(), "DGCNN_cls", 667).eval()
+    with torch.no_grad():
+        lg = cls(x.to(DEV))
+    assert_close(lg, golden("dgcnn_cls")["logits_eval"], 1e-3, "DGCNN_cls logits")
+
+
+def test_pointnet_g_golden(S, golden):
+    g = golden("pointnet_g")
+    x, _ = O.synth_clouds(2, 1024, 41)
+    pn = _load(S.Model.Net_MDA("Pointnet"), "Net_MDA:Pointnet", 668).train()
+    torch.manual_seed(17)
+    f, n, off = pn.g(x.to(DEV), node=True)
+    assert_close(f, g["feat"], 1e-3, "Pointnet feat")
+    assert_close(n, g["node_fea"], 1e-3, "Pointnet node_fea")
+    assert_close(off, g["node_off"], 1e-3, "Pointnet node_off")
+    assert_close(pn.g.conv5.conv[1].running_var, g["rv5"], 1e-3, "Pointnet rv5")
+
+
+def test_sug_step_golden(S, golden):
+    g = golden("sug_step")
+    Bs = 12
+    data, label = O.synth_clouds(Bs, 1024, 0)
+    data_t, label_t = O.synth_clouds(Bs, 1024, 1)
+    net = _load(S.Model.Net_MDA("DGCNN"), "Net_MDA:DGCNN").train()
+    for hd in (net.c1, net.c2):
+        hd.dropout1.p = hd.dropout2.p = 0.0
+    crit = S.model_utils.focal_loss(num_classes=10, gamma=0.0, alpha=[0.1] * 10)
+    torch.manual_seed(101)
+    r = S.step.sug_losses(net, data.to(DEV), label.to(DEV), data_t.to(DEV), label_t.to(DEV), crit)
+    r["loss"].backward()
+    for k in ("loss", "loss_cls", "loss_geo", "loss_sem"):
+        assert_close(r[k], g[k], 1e-3, k)
+    assert_close(r["pred_s1"], g["pred_s1"], 1e-3, "pred_s1")
+    assert_close(r["pred_t1"], g["pred_t1"], 1e-3, "pred_t1")
+    params = dict(net.named_parameters())
+    worst = ("", 0.0)
+    for k, v in g.items():
+        if k.startswith("gf."):
+            e = relerr(params[k[3:]].grad, v)
+            worst = max(worst, (k, e), key=lambda t: t[1])
+            assert e < 5e-3, f"grad {k}: rel err {e:.2e}"
+        elif k.startswith("gn."):
+            gn = float(params[k[3:]].grad.norm())
+            assert abs(gn - float(v)) <= 5e-3 * float(v) + 1e-7, f"grad norm {k}: {gn} vs {float(v)}"
+    print("worst full-gradient rel err:", worst)
+    assert params["g.input_transform_net.fc3.weight"].grad is None
+    assert params["g.node_fea_adapt.trans.conv.0.weight"].grad is None
+
+
+def test_full_size_properties(S):
+    """BASELINE config-2 sizes (B=64, N=1024): properties that need no CPU oracle."""
+    B, N, k = 64, 1024, 20
+    x, _ = O.synth_clouds(B, N, 0)
+    xg = x.to(DEV).squeeze(-1)
+    idx = S.ops.knn_cm(xg, k).long()
+    assert bool((idx[..., 0] == torch.arange(N, device=DEV)).all())
+    D = -(torch.cdist(xg.transpose(1, 2), xg.transpose(1, 2)) ** 2)
+    sel = torch.gather(D, 2, idx)
+    kth = sel.min(-1)[0]
+    mask = torch.ones_like(D, dtype=torch.bool).scatter_(2, idx, False)
+    best_out = torch.where(mask, D, torch.full_like(D, -1e30)).max(-1)[0]
+    assert bool((best_out <= kth + 2e-6).all()), "an excluded point is closer than the k-th neighbour"
+    # a feature kNN at C=64 + EdgeConv: permuting the neighbour slots must not change the output
+    f = feat_input(B, 64, N, 3).to(DEV).transpose(1, 2).contiguous()
+    idf = S.ops.knn_pm(f, k)
+    blk = S.model_utils.conv_2d(128, 64, 1, activation="leakyrelu", bias=False).to(DEV).train()
+    with torch.no_grad():
+        o1 = blk.edgeconv(f, idf)
+        o2 = blk.edgeconv(f, idf.flip(-1).contiguous())
+    assert float((o1 - o2).abs().max()) <= 1e-5 * float(o1.abs().max())
+    # BatchNorm: per-channel statistics of the pre-activation are (0, 1) => running_mean moved by 0.1*mean
+    assert int(blk.conv[1].num_batches_tracked) == 2
