@@ -155,6 +155,19 @@ int sug_gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64
                  const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
                  sug_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Launch accounting used by bench.py (`gpu_launches`, `roofline`).  Every kernel launch of the
+ * library is counted per kernel class together with its algorithmic flops / bytes (formulas in
+ * DESIGN.md).  sug_prof_enable(mask) additionally brackets the launches of the selected classes
+ * with CUDA events on their own stream; sug_prof_collect synchronises the device and returns, per
+ * class, the timed milliseconds, the number of timed launches, all launches, flops and bytes.
+ * ------------------------------------------------------------------------------------------- */
+int sug_prof_num_classes(void);
+const char* sug_prof_class_name(int i);
+void sug_prof_enable(unsigned mask);
+void sug_prof_reset(void);
+int sug_prof_collect(double* ms, long long* timed, long long* launches, double* flops, double* bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .model_utils import adapt_layer_off, conv_2d, fc_layer, transform_net
+from .model_utils import adapt_layer_off, conv_2d, exact_conv, fc_layer, transform_net
 
 K = 20  # Model.py:52
 
@@ -30,7 +30,8 @@ class CALayer(nn.Module):
         self.bn = nn.BatchNorm1d(4096)
 
     def forward(self, x):
-        y = self.conv_du(x)
+        with exact_conv():
+            y = self.conv_du(x)
         y = x * y + x
         y = y.view(y.shape[0], -1)
         return self.bn(y)
@@ -74,7 +75,8 @@ class DGCNN(nn.Module):
         x1 = self.conv1.edgeconv(x0, ops.knn_cm(x_loc, k))
         x2 = self.conv2.edgeconv(x1, ops.knn_pm(x1, k))
         x_, node_fea, node_off = self.node_fea_adapt(x2.transpose(1, 2).unsqueeze(3), x_loc)  # [B,64,N,1]
-        x2 = self.conv1d(x_.squeeze(-1)).transpose(1, 2).contiguous()
+        with exact_conv():
+            x2 = self.conv1d(x_.squeeze(-1)).transpose(1, 2).contiguous()
         x3 = self.conv3.edgeconv(x2, ops.knn_pm(x2, k))
         x4 = self.conv4.edgeconv(x3, ops.knn_pm(x3, k))
         feat = self._tail(torch.cat((x1, x2, x3, x4), dim=2))

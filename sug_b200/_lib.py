@@ -40,6 +40,11 @@ SIGNATURES = {
     "sug_knn_query": (I, [P, P, I, I, I, I, P, P]),
     "sug_three_nn": (I, [P, P, I, I, I, I, P, P]),
     "sug_gemm_f32": (I, [P, L, L, P, L, L, P, P, L, I, I, I, I, P]),
+    "sug_prof_num_classes": (I, []),
+    "sug_prof_class_name": (c_char_p, [I]),
+    "sug_prof_enable": (None, [ctypes.c_uint]),
+    "sug_prof_reset": (None, []),
+    "sug_prof_collect": (I, [P, P, P, P, P]),
 }
 
 
@@ -80,3 +85,23 @@ def check(status: int, what: str):
     if status != 0:
         msg = load().sug_last_error().decode(errors="replace")
         raise SugError(f"{what} failed with status {status}: {msg}")
+
+
+def prof_reset(mask: int = 0):
+    lib = load()
+    lib.sug_prof_reset()
+    lib.sug_prof_enable(mask)
+
+
+def prof_collect():
+    """{class name: dict(ms, timed, launches, flops, bytes)} since the last prof_reset()."""
+    lib = load()
+    n = lib.sug_prof_num_classes()
+    D, LL = ctypes.c_double * n, ctypes.c_longlong * n
+    ms, timed, launches, flops, byts = D(), LL(), LL(), D(), D()
+    check(lib.sug_prof_collect(ms, timed, launches, flops, byts), "sug_prof_collect")
+    out = {}
+    for i in range(n):
+        out[lib.sug_prof_class_name(i).decode()] = dict(index=i, ms=ms[i], timed=timed[i], launches=launches[i],
+                                                        flops=flops[i], bytes=byts[i])
+    return out

@@ -204,6 +204,7 @@ extern "C" int sug_fps(const float* xyz, int B, int N, int npoint, const int32_t
     configured = smem;
   }
   int nt = N >= 1024 ? 1024 : ((N + 31) / 32) * 32;
+  ProfScope ps(KC_ADAPT, 0, 0, (cudaStream_t)stream);
   fps_kernel<<<B, nt, smem, (cudaStream_t)stream>>>(xyz, N, npoint, start, out_idx);
   SUG_LAUNCH_CHECK();
   return 0;
@@ -215,6 +216,7 @@ extern "C" int sug_ball_query(const float* xyz, const float* query, int B, int N
   SUG_CHECK_ARG(B > 0 && N > 0 && S > 0 && nsample > 0, "ball_query: bad shape");
   const float r2 = (float)((double)radius * (double)radius);
   dim3 grid(cdiv((long long)S * 32, 256), B);
+  ProfScope ps(KC_ADAPT, 0, 0, (cudaStream_t)stream);
   ball_query_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyz, query, N, S, r2, nsample, out_idx);
   SUG_LAUNCH_CHECK();
   return 0;
@@ -234,6 +236,7 @@ extern "C" int sug_knn_query(const float* xyz, const float* query, int B, int N,
     configured = smem;
   }
   int nt = np2 / 2 < 512 ? (np2 / 2 < 32 ? 32 : np2 / 2) : 512;
+  ProfScope ps(KC_ADAPT, 0, 0, (cudaStream_t)stream);
   knn_query_kernel<<<dim3(S, B), nt, smem, (cudaStream_t)stream>>>(xyz, query, N, S, np2, nsample, out_idx);
   SUG_LAUNCH_CHECK();
   return 0;
@@ -245,6 +248,7 @@ extern "C" int sug_three_nn(const float* xyz, const float* nodes, int B, int N, 
   SUG_CHECK_ARG(B > 0 && N > 0 && M > 0 && k > 0 && k <= 8 && k <= M, "three_nn: bad shape");
   size_t smem = sizeof(float) * 4 * (size_t)M;
   SUG_CHECK_ARG(smem <= 48 * 1024, "three_nn: M=%d too large", M);
+  ProfScope ps(KC_ADAPT, 0, 0, (cudaStream_t)stream);
   three_nn_kernel<<<dim3(cdiv(N, 256), B), 256, smem, (cudaStream_t)stream>>>(xyz, nodes, N, M, k, out_idx);
   SUG_LAUNCH_CHECK();
   return 0;

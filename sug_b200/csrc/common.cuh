@@ -51,6 +51,21 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 int num_sms();
 
+// ---- launch accounting / optional per-kernel-class CUDA-event timing (bench.py roofline) -------
+enum KClass {
+  KC_GEMM = 0, KC_KNN, KC_KNN_REV, KC_EDGE_FWD, KC_BN_ACT, KC_EDGE_BWD_PRE, KC_EDGE_BWD_MAIN, KC_COLSTATS,
+  KC_POOL_FWD, KC_POOL_BWD, KC_MMD, KC_CHAMFER, KC_ADAPT, KC_MISC, KC_GEMM_TC, KC_KNN_TC, KC_NUM
+};
+// Counts one kernel launch of class `cls` with its algorithmic flops / bytes (DESIGN.md states the
+// formulas); when timing of the class is enabled, brackets the launch with CUDA events on `stream`.
+struct ProfScope {
+  int cls;
+  cudaStream_t stream;
+  int slot;
+  ProfScope(int cls, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+};
+
 // Simple bump allocator over the caller's workspace.
 struct Workspace {
   char* base;

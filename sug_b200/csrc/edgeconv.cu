@@ -348,26 +348,38 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
   float* mi_eval = W.take<float>(2 * (size_t)Cout);
   if (!W.ok()) { set_error("edgeconv_fwd: workspace too small (%zu B)", ws_bytes); return SUG_E_WORKSPACE; }
 
-  edge_pack_weight_kernel<<<cdiv((long long)Cout * C, 256), 256, 0, stream>>>(w, C, Cout, wcat);
+  {
+    ProfScope ps(KC_MISC, 0, 0, stream);
+    edge_pack_weight_kernel<<<cdiv((long long)Cout * C, 256), 256, 0, stream>>>(w, C, Cout, wcat);
+  }
   SUG_LAUNCH_CHECK();
   SUG_TRY(gemm_f32(x, ldx, 1, wcat, C, 1, nullptr, ab, 2 * Cout, (int)P, 2 * Cout, C, 0, stream));
   const int grid = gather_grid(P, Cout);
   if (training) {
     SUG_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cout, stream));
-    edge_gather_fwd_kernel<true><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, nullptr, (int)P, N, k, Cout, slope,
-                                                           ext, arg, ssum, sums, nullptr, 0);
+    {
+      ProfScope ps(KC_EDGE_FWD, 4.0 * P * k * Cout, (double)P * (8.0 * Cout + 4.0 * k + 9.0 * Cout), stream);
+      edge_gather_fwd_kernel<true><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, nullptr, (int)P, N, k, Cout, slope,
+                                                             ext, arg, ssum, sums, nullptr, 0);
+    }
     SUG_LAUNCH_CHECK();
     SUG_TRY(bn_finalize_stats(sums, Cout, (double)P * k, eps, momentum, running_mean, running_var,
                               save_mean_invstd, stream));
     long long total = P * (Cout >> 2);
     int g2 = (int)min((long long)num_sms() * 8, (total + 255) / 256);
-    bn_act_kernel<<<g2, 256, 2 * Cout * sizeof(float), stream>>>(ext, gamma, beta, save_mean_invstd, P, Cout, slope,
-                                                                 out, ldo);
+    {
+      ProfScope ps(KC_BN_ACT, 2.0 * P * Cout, 8.0 * P * Cout, stream);
+      bn_act_kernel<<<g2, 256, 2 * Cout * sizeof(float), stream>>>(ext, gamma, beta, save_mean_invstd, P, Cout, slope,
+                                                                   out, ldo);
+    }
     SUG_LAUNCH_CHECK();
   } else {
     SUG_TRY(bn_eval_stats(running_mean, running_var, Cout, eps, mi_eval, stream));
-    edge_gather_fwd_kernel<false><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, mi_eval, (int)P, N, k, Cout, slope,
-                                                            nullptr, nullptr, nullptr, nullptr, out, ldo);
+    {
+      ProfScope ps(KC_EDGE_FWD, 2.0 * P * k * Cout, (double)P * (8.0 * Cout + 4.0 * k + 4.0 * Cout), stream);
+      edge_gather_fwd_kernel<false><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, mi_eval, (int)P, N, k, Cout, slope,
+                                                              nullptr, nullptr, nullptr, nullptr, out, ldo);
+    }
     SUG_LAUNCH_CHECK();
   }
   return 0;
@@ -396,18 +408,30 @@ extern "C" int sug_edgeconv_bwd(const float* gout, int64_t ldg, const float* x, 
 
   SUG_CUDA(cudaMemsetAsync(gsums, 0, sizeof(double) * 2 * Cout, stream));
   const int grid = gather_grid(P, Cout);
-  edge_bwd_pre_kernel<<<grid, 256, 0, stream>>>(gout, ldg, ext, gamma, beta, save_mean_invstd, P, Cout, slope, ghat,
-                                                gsums);
+  {
+    ProfScope ps(KC_EDGE_BWD_PRE, 6.0 * P * Cout, 12.0 * P * Cout, stream);
+    edge_bwd_pre_kernel<<<grid, 256, 0, stream>>>(gout, ldg, ext, gamma, beta, save_mean_invstd, P, Cout, slope, ghat,
+                                                  gsums);
+  }
   SUG_LAUNCH_CHECK();
-  edge_bwd_main_kernel<<<grid, 256, 0, stream>>>(ab, ghat, arg, ssum, rev_ptr, rev_edge, gamma, save_mean_invstd,
-                                                 gsums, P, N, k, Cout, dab, dgamma, dbeta);
+  {
+    ProfScope ps(KC_EDGE_BWD_MAIN, 3.0 * P * k * Cout, (double)P * (8.0 * Cout + 9.0 * Cout + 4.0 * k + 8.0 * Cout), stream);
+    edge_bwd_main_kernel<<<grid, 256, 0, stream>>>(ab, ghat, arg, ssum, rev_ptr, rev_edge, gamma, save_mean_invstd,
+                                                   gsums, P, N, k, Cout, dab, dgamma, dbeta);
+  }
   SUG_LAUNCH_CHECK();
   // dWcat = dab^T x   ([2Cout, P] x [P, C])
   SUG_TRY(gemm_f32(dab, 1, 2 * Cout, x, 1, ldx, nullptr, dwcat, C, 2 * Cout, C, (int)P, 0, stream));
-  edge_unpack_wgrad_kernel<<<cdiv((long long)Cout * C, 256), 256, 0, stream>>>(dwcat, C, Cout, dw);
+  {
+    ProfScope ps(KC_MISC, 0, 0, stream);
+    edge_unpack_wgrad_kernel<<<cdiv((long long)Cout * C, 256), 256, 0, stream>>>(dwcat, C, Cout, dw);
+  }
   SUG_LAUNCH_CHECK();
   if (dx != nullptr) {
-    edge_pack_weight_kernel<<<cdiv((long long)Cout * C, 256), 256, 0, stream>>>(w, C, Cout, wcat);
+    {
+      ProfScope ps(KC_MISC, 0, 0, stream);
+      edge_pack_weight_kernel<<<cdiv((long long)Cout * C, 256), 256, 0, stream>>>(w, C, Cout, wcat);
+    }
     SUG_LAUNCH_CHECK();
     // dx = dab * Wcat   ([P, 2Cout] x [2Cout, C])
     SUG_TRY(gemm_f32(dab, 2 * Cout, 1, wcat, 1, C, nullptr, dx, lddx, (int)P, C, 2 * Cout, accumulate_dx, stream));

@@ -124,6 +124,7 @@ int gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t s
   if (use_atomic && !accumulate)
     SUG_CUDA(cudaMemset2DAsync(c, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
   dim3 grid(tn, tm, splits);
+  ProfScope ps(KC_GEMM, 2.0 * M * (double)N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N), stream);
   const bool akc = (sak == 1), bkc = (sbk == 1);
 #define SUG_GEMM_LAUNCH(AK, BK_)                                                                             \
   gemm_simt_kernel<AK, BK_><<<grid, 256, 0, stream>>>(a, sam, sak, b, sbn, sbk, bias, c, ldc, M, N, K, kchunk, \

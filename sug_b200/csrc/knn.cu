@@ -215,6 +215,7 @@ int knn_simt(const float* x, int B, int C, int N, int k, long long sb, long long
     configured = smem;
   }
   dim3 grid(cdiv(N, KTM), B);
+  ProfScope ps(KC_KNN, 2.0 * B * (double)N * N * C, 4.0 * B * (double)N * (C + k), stream);
   knn_simt_kernel<<<grid, KTM, smem, stream>>>(x, C, N, k, sb, sn, sc, idx);
   SUG_LAUNCH_CHECK();
   return 0;
@@ -324,6 +325,7 @@ extern "C" int sug_knn_reverse(const int32_t* idx, int B, int N, int k, int32_t*
     SUG_CUDA(cudaFuncSetAttribute(sug::knn_reverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  sug::ProfScope ps(sug::KC_KNN_REV, 0, 4.0 * B * ((double)N * k * 2 + N + 1), (cudaStream_t)stream);
   sug::knn_reverse_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(idx, N, k, rev_ptr, rev_edge);
   SUG_LAUNCH_CHECK();
   return 0;

@@ -139,9 +139,15 @@ extern "C" int sug_mmd_rbf_fwd(const float* z, int64_t ldz, int m, int D, const 
   const int n2 = 2 * m;
   SUG_TRY(gemm_f32(z, ldz, 1, z, ldz, 1, nullptr, G, n2, n2, n2, D, 0, stream));
   SUG_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), stream));
-  mmd_coef_kernel<<<n2, 128, 0, stream>>>(G, m, sg, weights, biased, coef, acc);
+  {
+    ProfScope ps(KC_MMD, 12.0 * nsig * n2 * (double)n2, 8.0 * n2 * (double)n2, stream);
+    mmd_coef_kernel<<<n2, 128, 0, stream>>>(G, m, sg, weights, biased, coef, acc);
+  }
   SUG_LAUNCH_CHECK();
-  mmd_finalize_kernel<<<1, 1, 0, stream>>>(acc, loss);
+  {
+    ProfScope ps(KC_MISC, 0, 0, stream);
+    mmd_finalize_kernel<<<1, 1, 0, stream>>>(acc, loss);
+  }
   SUG_LAUNCH_CHECK();
   return 0;
 }
@@ -154,6 +160,7 @@ extern "C" int sug_mmd_rbf_bwd(const float* z, int64_t ldz, int m, int D, const 
   // dz = coef * z   ([2m, 2m] x [2m, D]),  then scaled by 2 * gloss
   SUG_TRY(gemm_f32(coef, n2, 1, z, 1, ldz, nullptr, dz, lddz, n2, D, n2, 0, stream));
   long long total = (long long)n2 * D;
+  ProfScope ps(KC_MISC, 0, 0, stream);
   scale_rows_kernel<<<(int)min((long long)num_sms() * 4, (total + 255) / 256), 256, 0, stream>>>(dz, lddz, n2, D, gloss,
                                                                                                2.f);
   SUG_LAUNCH_CHECK();
@@ -165,6 +172,7 @@ extern "C" int sug_chamfer_f32(const float* p1, const float* p2, int B, int N, i
   SUG_CHECK_ARG(p1 && p2 && d1 && d2, "chamfer: null pointer");
   SUG_CHECK_ARG(B > 0 && N > 0 && M > 0, "chamfer: bad shape");
   dim3 grid(cdiv(N > M ? N : M, 128), B, 2);
+  ProfScope ps(KC_CHAMFER, 16.0 * B * (double)N * M, 12.0 * B * (N + M) + 4.0 * B * (N + M), (cudaStream_t)stream_);
   chamfer_kernel<<<grid, 128, 0, (cudaStream_t)stream_>>>(p1, p2, N, M, d1, d2);
   SUG_LAUNCH_CHECK();
   return 0;

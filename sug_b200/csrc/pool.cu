@@ -268,7 +268,10 @@ extern "C" int sug_mlp_pool_fwd(const float* x, int64_t ldx, const float* w, con
   if (training) {
     SUG_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cout, stream));
     int gy = (int)min((long long)num_sms() * 4 / gx + 1, (P + PRL - 1) / PRL);
-    col_stats_kernel<<<dim3(gx, gy), 256, 0, stream>>>(y, P, Cout, sums);
+    {
+      ProfScope ps(KC_COLSTATS, 3.0 * P * Cout, 4.0 * P * Cout, stream);
+      col_stats_kernel<<<dim3(gx, gy), 256, 0, stream>>>(y, P, Cout, sums);
+    }
     SUG_LAUNCH_CHECK();
     SUG_TRY(bn_finalize_stats(sums, Cout, (double)P, eps, momentum, running_mean, running_var, save_mean_invstd,
                               stream));
@@ -276,7 +279,10 @@ extern "C" int sug_mlp_pool_fwd(const float* x, int64_t ldx, const float* w, con
     SUG_TRY(bn_eval_stats(running_mean, running_var, Cout, eps, mi_eval, stream));
     mi = mi_eval;
   }
-  pool_fwd_kernel<<<dim3(gx, B), 256, 0, stream>>>(y, gamma, beta, mi, N, Cout, slope, pool, out, argext);
+  {
+    ProfScope ps(KC_POOL_FWD, 5.0 * P * Cout, 4.0 * P * Cout, stream);
+    pool_fwd_kernel<<<dim3(gx, B), 256, 0, stream>>>(y, gamma, beta, mi, N, Cout, slope, pool, out, argext);
+  }
   SUG_LAUNCH_CHECK();
   return 0;
 }
@@ -297,11 +303,17 @@ extern "C" int sug_mlp_pool_bwd(const float* gout, const float* x, int64_t ldx, 
   if (!W.ok()) { set_error("mlp_pool_bwd: workspace too small"); return SUG_E_WORKSPACE; }
   SUG_CUDA(cudaMemsetAsync(gsums, 0, sizeof(double) * 2 * Cout, stream));
   const int gx = cdiv(Cout, PCQ * 4);
-  pool_bwd_pre_kernel<<<dim3(gx, B), 256, 0, stream>>>(y, gout, argext, gamma, beta, save_mean_invstd, N, Cout,
-                                                       slope, pool, gsums);
+  {
+    ProfScope ps(KC_POOL_BWD, 8.0 * P * Cout, 4.0 * P * Cout, stream);
+    pool_bwd_pre_kernel<<<dim3(gx, B), 256, 0, stream>>>(y, gout, argext, gamma, beta, save_mean_invstd, N, Cout,
+                                                         slope, pool, gsums);
+  }
   SUG_LAUNCH_CHECK();
-  pool_bwd_main_kernel<<<dim3(gx, B), 256, 0, stream>>>(y, gout, argext, gamma, beta, save_mean_invstd, gsums, B, N,
-                                                        Cout, slope, pool, dgamma, dbeta);
+  {
+    ProfScope ps(KC_POOL_BWD, 10.0 * P * Cout, 8.0 * P * Cout, stream);
+    pool_bwd_main_kernel<<<dim3(gx, B), 256, 0, stream>>>(y, gout, argext, gamma, beta, save_mean_invstd, gsums, B, N,
+                                                          Cout, slope, pool, dgamma, dbeta);
+  }
   SUG_LAUNCH_CHECK();
   // a per-channel constant added before train-mode BatchNorm has zero gradient
   if (dbias != nullptr) SUG_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, stream));

@@ -264,14 +264,30 @@ def test_mmd_golden(S, golden):
     v = S.mmd.mix_rbf_mmd2(Xg, Yg, S.mmd.sigma_list, sample_weights=d(w))
     v.backward()
     assert_close(v, g["v_w"], 1e-4, "mmd weighted")
-    assert_close(Xg.grad, g["dX"], 1e-3, "mmd dX")
-    assert_close(Yg.grad, g["dY"], 1e-3, "mmd dY")
+    # Gradients: the reference's fp32 autograd cancels catastrophically on the Gram diagonal
+    # (oracle/sug_oracle.py:mmd_cal docstring), so the fixture's dX is itself far from the exact
+    # gradient.  The kernel must match the fp64 evaluation of the same loss; the fixture's own
+    # error against fp64 is reported and bounds the kernel-vs-fixture distance (triangle).
+    def truth(A, Bm, scale=1.0):
+        A64, B64 = A.double().requires_grad_(True), Bm.double().requires_grad_(True)
+        (scale * O.mix_rbf_mmd2(A64, B64, sample_weights=w.double())).backward()
+        return A64.grad, B64.grad
+    tX, tY = truth(X, Y)
+    e_fix = relerr(torch.from_numpy(g["dX"]), tX)
+    print(f"mmd dX (4096-d): kernel vs fp64 {relerr(Xg.grad, tX):.2e}; reference fp32 fixture vs fp64 {e_fix:.2e}")
+    assert_close(Xg.grad, tX, 1e-3, "mmd dX vs fp64")
+    assert_close(Yg.grad, tY, 1e-3, "mmd dY vs fp64")
+    assert relerr(Xg.grad, g["dX"]) <= 1.1 * e_fix + 1e-3
     Xsg, Ysg = d(Xs).requires_grad_(True), d(Ys).requires_grad_(True)
     v = S.mmd.mix_rbf_mmd2(Xsg, Ysg, S.mmd.sigma_list, sample_weights=d(w))
     (3.0 * v).backward()
     assert_close(v, g["v_sem"], 1e-4, "mmd sem")
-    assert_close(Xsg.grad, 3.0 * g["dXs"], 1e-3, "mmd dXs")
-    assert_close(Ysg.grad, 3.0 * g["dYs"], 1e-3, "mmd dYs")
+    tXs, tYs = truth(Xs, Ys, 3.0)
+    e_fix = relerr(3.0 * torch.from_numpy(g["dXs"]), tXs)
+    print(f"mmd dX (256-d): kernel vs fp64 {relerr(Xsg.grad, tXs):.2e}; reference fp32 fixture vs fp64 {e_fix:.2e}")
+    assert_close(Xsg.grad, tXs, 1e-3, "mmd dXs vs fp64")
+    assert_close(Ysg.grad, tYs, 1e-3, "mmd dYs vs fp64")
+    assert relerr(Xsg.grad, 3.0 * g["dXs"]) <= 1.1 * e_fix + 1e-3
     assert_close(S.mmd.geometric_weights(d(ds), d(dt), weighting="mean2one"), g["geo_w"], 1e-4, "geo weights")
     assert_close(S.mmd.prob_weights_soft(d(ps), d(pt), d(ls), d(lt), 0.5, "mean2one"), g["sem_w"], 1e-3, "sem weights")
     assert_close(S.mmd.mmd_cal(d(ls), d(X), d(lt), d(Y), O.SUG_CFG["GEO_MMD"], data_s=d(ds), data_t=d(dt)), g["geo"],
@@ -289,7 +305,8 @@ def test_mmd_unbiased_and_sizes(S):
         X = torch.from_numpy(rng.standard_normal((m, D)).astype(np.float32) * 0.3)
         Y = torch.from_numpy(rng.standard_normal((m, D)).astype(np.float32) * 0.35)
         for biased in (True, False):
-            Xo, Yo = X.clone().requires_grad_(True), Y.clone().requires_grad_(True)
+            # fp64 evaluation of the reference formula (see test_mmd_golden for why not fp32)
+            Xo, Yo = X.double().requires_grad_(True), Y.double().requires_grad_(True)
             vo = O.mix_rbf_mmd2(Xo, Yo, biased=biased)
             vo.backward()
             Xg, Yg = X.to(DEV).requires_grad_(True), Y.to(DEV).requires_grad_(True)
@@ -422,16 +439,30 @@ def test_sug_step_golden(S, golden):
     assert_close(r["pred_s1"], g["pred_s1"], 1e-3, "pred_s1")
     assert_close(r["pred_t1"], g["pred_t1"], 1e-3, "pred_t1")
     params = dict(net.named_parameters())
-    worst = ("", 0.0)
-    for k, v in g.items():
-        if k.startswith("gf."):
-            e = relerr(params[k[3:]].grad, v)
-            worst = max(worst, (k, e), key=lambda t: t[1])
-            assert e < 5e-3, f"grad {k}: rel err {e:.2e}"
-        elif k.startswith("gn."):
-            gn = float(params[k[3:]].grad.norm())
-            assert abs(gn - float(v)) <= 5e-3 * float(v) + 1e-7, f"grad norm {k}: {gn} vs {float(v)}"
-    print("worst full-gradient rel err:", worst)
+    # Gradients are judged against the oracle with the MMD autograd evaluated in fp64: the
+    # reference's fp32 MMD backward is dominated by cancellation noise (see test_mmd_golden), which
+    # contaminates every parameter upstream of the MMD losses in the fixture.
+    sd = O.clone_state(O.synth_state("Net_MDA:DGCNN"), requires_grad=True)
+    torch.manual_seed(101)
+    ro = O.sug_losses(sd, data, label, data_t, label_t, O.FocalLoss([0.1] * 10, 0.0), drop_p=0.0,
+                      mmd_dtype=torch.float64)
+    ro["loss"].backward()
+    assert_close(r["loss"], ro["loss"], 1e-3, "loss vs oracle")
+    worst, worst_fix = ("", 0.0), ("", 0.0)
+    n = 0
+    for k, p in params.items():
+        go = sd[k].grad
+        if go is None:
+            assert p.grad is None, f"{k} has a gradient here but not in the reference"
+            continue
+        e = relerr(p.grad, go)
+        worst = max(worst, (k, e), key=lambda t: t[1])
+        n += 1
+        if "gf." + k in g:
+            worst_fix = max(worst_fix, (k, relerr(p.grad, g["gf." + k])), key=lambda t: t[1])
+    print(f"{n} parameter gradients; worst rel err vs oracle(fp64 MMD): {worst}; vs fp32 reference fixture: {worst_fix}")
+    assert worst[1] < 5e-3, f"gradient of {worst[0]}: rel err {worst[1]:.2e}"
+    assert n >= 50
     assert params["g.input_transform_net.fc3.weight"].grad is None
     assert params["g.node_fea_adapt.trans.conv.0.weight"].grad is None
 
