@@ -155,6 +155,15 @@ int sug_gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64
                  const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
                  sug_stream_t stream);
 
+/* fp32-accurate tensor-core GEMM (tcgen05 kind::tf32, 3-term hi/lo split, TMA-fed, TMEM
+ * accumulators): C[M,N] = A * B^T (+ bias).  a_mn_major == 0: a is [M,K] row-major (stride lda);
+ * a_mn_major != 0: a is [K,M] row-major (stride lda), i.e. the operand is consumed transposed; same
+ * for b / N.  Bases must be 16 B aligned and lda / ldb multiples of 4.  Exported for tests; the
+ * entry points above use it internally for every GEMM with K >= 16. */
+int sug_gemm_tc_f32(const float* a, int64_t lda, int a_mn_major, const float* b, int64_t ldb,
+                    int b_mn_major, const float* bias, float* c, int64_t ldc, int M, int N, int K,
+                    sug_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Launch accounting used by bench.py (`gpu_launches`, `roofline`).  Every kernel launch of the
  * library is counted per kernel class together with its algorithmic flops / bytes (formulas in

@@ -55,9 +55,15 @@ def pairwise_neg_sqdist(x: torch.Tensor) -> torch.Tensor:
     return -xx - inner - xx.transpose(2, 1)
 
 
+KNN_TRACE = None  # set to a list to record every neighbour list knn() returns (teacher forcing in tests)
+
+
 def knn(x: torch.Tensor, k: int) -> torch.Tensor:
     """model_utils.py:178-185.  int64 [B,N,k], nearest first, self included."""
-    return pairwise_neg_sqdist(x).topk(k=k, dim=-1)[1]
+    idx = pairwise_neg_sqdist(x).topk(k=k, dim=-1)[1]
+    if KNN_TRACE is not None:
+        KNN_TRACE.append(idx)
+    return idx
 
 
 def get_graph_feature(x: torch.Tensor, k: int = 20, idx: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -40,6 +40,7 @@ SIGNATURES = {
     "sug_knn_query": (I, [P, P, I, I, I, I, P, P]),
     "sug_three_nn": (I, [P, P, I, I, I, I, P, P]),
     "sug_gemm_f32": (I, [P, L, L, P, L, L, P, P, L, I, I, I, I, P]),
+    "sug_gemm_tc_f32": (I, [P, L, I, P, L, I, P, P, L, I, I, I, P]),
     "sug_prof_num_classes": (I, []),
     "sug_prof_class_name": (c_char_p, [I]),
     "sug_prof_enable": (None, [ctypes.c_uint]),

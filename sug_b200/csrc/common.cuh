@@ -101,9 +101,16 @@ __device__ __forceinline__ float act_leaky(float z, float slope) { return z > 0.
 __device__ __forceinline__ float act_leaky_grad(float z, float slope) { return z > 0.f ? 1.f : slope; }
 
 // internal launchers shared between translation units -----------------------------------------
+// C[M,N] (+)= A B^T (+bias) with A(m,k) = a[m*sam + k*sak], B(n,k) = b[n*sbn + k*sbk]: dispatches to the
+// tcgen05 3xTF32 kernel (gemm_tc.cu) or the exact-fp32 CUDA-core kernel (gemm.cu).
 int gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
              const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
              cudaStream_t stream);
+int gemm_simt_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
+                  const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
+                  cudaStream_t stream);
+int gemm_tc_f32(const float* a, int64_t lda, int a_mn, const float* b, int64_t ldb, int b_mn, const float* bias,
+                float* c, int64_t ldc, int M, int N, int K, cudaStream_t stream);
 
 // Per-channel BatchNorm batch statistics -> (mean, invstd), running-stat update.
 // sums: [2*C] doubles (sum, sum of squares) over `count` samples.

@@ -106,9 +106,9 @@ gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, cons
   }
 }
 
-int gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
-             const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
-             cudaStream_t stream) {
+int gemm_simt_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
+                  const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
+                  cudaStream_t stream) {
   SUG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   SUG_CHECK_ARG(a && b && c, "gemm: null operand");
   const int tm = cdiv(M, GBM), tn = cdiv(N, GBN);
@@ -138,10 +138,30 @@ int gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t s
   return 0;
 }
 
+// Dispatcher used by every entry point: the tcgen05 3xTF32 kernel whenever the operands satisfy
+// the TMA constraints (unit stride on one axis, 16 B aligned base, leading dimension % 4 == 0) and
+// the reduction is long enough to feed the tensor core; the CUDA-core kernel otherwise (xyz layers
+// with K = 3, ragged leading dimensions such as the 4106-wide MMD features, accumulate mode).
+int gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
+             const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
+             cudaStream_t stream) {
+  auto tma_ok = [](const float* p, int64_t s_row, int64_t s_k, int* mn, int64_t* ld) {
+    if (s_k == 1) { *mn = 0; *ld = s_row; }
+    else if (s_row == 1) { *mn = 1; *ld = s_k; }
+    else return false;
+    return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (*ld % 4) == 0 && *ld > 0;
+  };
+  int a_mn = 0, b_mn = 0;
+  int64_t lda = 0, ldb = 0;
+  if (!accumulate && K >= 16 && N >= 8 && tma_ok(a, sam, sak, &a_mn, &lda) && tma_ok(b, sbn, sbk, &b_mn, &ldb))
+    return gemm_tc_f32(a, lda, a_mn, b, ldb, b_mn, bias, c, ldc, M, N, K, stream);
+  return gemm_simt_f32(a, sam, sak, b, sbn, sbk, bias, c, ldc, M, N, K, accumulate, stream);
+}
+
 }  // namespace sug
 
 extern "C" int sug_gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
                             const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
                             sug_stream_t stream) {
-  return sug::gemm_f32(a, sam, sak, b, sbn, sbk, bias, c, ldc, M, N, K, accumulate, (cudaStream_t)stream);
+  return sug::gemm_simt_f32(a, sam, sak, b, sbn, sbk, bias, c, ldc, M, N, K, accumulate, (cudaStream_t)stream);
 }

@@ -1,0 +1,332 @@
+// fp32-accurate tensor-core GEMM for sm_100a:  C[M,N] (+)= A * B^T (+ bias),  3xTF32 split.
+//
+//   x = hi + lo,  hi = top 19 bits of the fp32 container (what kind::tf32 reads), lo = x - hi (exact)
+//   A B^T ~= lo(A) hi(B)^T + hi(A) lo(B)^T + hi(A) hi(B)^T        (error ~2^-21 |a||b| per product)
+//
+// Persistent, warp-specialised CTA (one per SM, 320 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor loads of the raw fp32 A / B k-blocks (128 B rows,
+//               SWIZZLE_128B) into a multi-stage ring; out-of-bounds rows / k read as zero
+//   warps 2-5   split: read each landed stage, write the `lo` tiles next to the raw ones
+//   warp 1      one elected thread issues 3 tcgen05.mma.kind::tf32 per 8-wide k-step into a TMEM
+//               accumulator (128 lanes x BN columns, double buffered), tcgen05.commit frees the stage
+//   warps 6-9   epilogue: tcgen05.ld the finished accumulator, add bias, store / atomically add to C
+// Both operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the latter
+// serves the weight-gradient reductions dY^T X without materialising transposes.
+#include "tc_common.cuh"
+
+namespace sug {
+
+using namespace tc;
+
+constexpr int TBM = 128;  // UMMA M (TMEM lanes)
+constexpr int TBK = 32;   // fp32 per k-block = one 128 B swizzle row
+constexpr int TC_THREADS = 320;
+
+enum { EPI_STORE = 0, EPI_ATOMIC = 1 };
+
+template <int BN>
+struct TcCfg {
+  static constexpr int A_BYTES = TBM * TBK * 4;  // 16 KB
+  static constexpr int B_BYTES = BN * TBK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct TcArgs {
+  float* C;
+  const float* bias;
+  long long ldc;
+  int M, N, K;
+  int tiles_m, tiles_n, ksplits, kb_per_split;
+  int epi;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int S = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;            // [S]  TMA -> split
+  uint64_t* ready = bars + S;       // [S]  split -> MMA
+  uint64_t* empty = bars + 2 * S;   // [S]  MMA -> TMA
+  uint64_t* tfull = bars + 3 * S;   // [2]  MMA -> epilogue
+  uint64_t* tempty = bars + 3 * S + 2;  // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.ksplits;
+  const int kb_total = (p.K + TBK - 1) / TBK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto stage_ptr = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES; };
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.tiles_n, mt = (t / p.tiles_n) % p.tiles_m, ks = t / (p.tiles_n * p.tiles_m);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+          uint8_t* sp = stage_ptr(s);
+          mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sp, &tmA, &full[s], kb * TBK, mt * TBM);
+          } else {
+#pragma unroll
+            for (int mb = 0; mb < TBM / 32; ++mb)
+              tma_load_2d(sp + mb * 4096, &tmA, &full[s], mt * TBM + mb * 32, kb * TBK);
+          }
+          uint8_t* bp = sp + 2 * Cfg::A_BYTES;
+          if (!B_MN) {
+            tma_load_2d(bp, &tmB, &full[s], kb * TBK, nt * BN);
+          } else {
+#pragma unroll
+            for (int nb = 0; nb < BN / 32; ++nb)
+              tma_load_2d(bp + nb * 4096, &tmB, &full[s], nt * BN + nb * 32, kb * TBK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(TBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      uint32_t it = 0, tile_it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+        const int ks = t / (p.tiles_n * p.tiles_m);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(kb_total, kb0 + p.kb_per_split);
+        const int ab = tile_it & 1;
+        mbar_wait(&tempty[ab], ((tile_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + ab * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(&ready[s], (it / S) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(stage_ptr(s));
+          const uint32_t a_lo = a_hi + Cfg::A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * Cfg::A_BYTES;
+          const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+          for (int j = 0; j < TBK / 8; ++j) {
+            const uint32_t ao = A_MN ? j * 1024 : j * 32;
+            const uint32_t bo = B_MN ? j * 1024 : j * 32;
+            const uint64_t dah = A_MN ? smem_desc_mnmajor(a_hi + ao, 4096) : smem_desc_kmajor(a_hi + ao);
+            const uint64_t dal = A_MN ? smem_desc_mnmajor(a_lo + ao, 4096) : smem_desc_kmajor(a_lo + ao);
+            const uint64_t dbh = B_MN ? smem_desc_mnmajor(b_hi + bo, 4096) : smem_desc_kmajor(b_hi + bo);
+            const uint64_t dbl = B_MN ? smem_desc_mnmajor(b_lo + bo, 4096) : smem_desc_kmajor(b_lo + bo);
+            mma_tf32(tacc, dal, dbh, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+            mma_tf32(tacc, dah, dbl, idesc, 1u);
+            mma_tf32(tacc, dah, dbh, idesc, 1u);
+          }
+          mma_commit(&empty[s]);
+        }
+        mma_commit(&tfull[ab]);
+      }
+    }
+  } else if (warp < 6) {
+    // ===================================== hi/lo split ========================================
+    const int tix = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int ks = t / (p.tiles_n * p.tiles_m);
+      const int kb0 = ks * p.kb_per_split, kb1 = min(kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(&full[s], (it / S) & 1);
+        uint8_t* sp = stage_ptr(s);
+        const float4* a_hi = reinterpret_cast<const float4*>(sp);
+        float4* a_lo = reinterpret_cast<float4*>(sp + Cfg::A_BYTES);
+        const float4* b_hi = reinterpret_cast<const float4*>(sp + 2 * Cfg::A_BYTES);
+        float4* b_lo = reinterpret_cast<float4*>(sp + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+        for (int i = 0; i < Cfg::A_BYTES / 16 / 128; ++i) {
+          float4 v = a_hi[tix + i * 128];
+          a_lo[tix + i * 128] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
+        }
+#pragma unroll
+        for (int i = 0; i < Cfg::B_BYTES / 16 / 128; ++i) {
+          float4 v = b_hi[tix + i * 128];
+          b_lo[tix + i * 128] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&ready[s]);
+      }
+    }
+  } else {
+    // ===================================== epilogue ===========================================
+    const int lg = warp & 3;  // TMEM lane group this warp may access
+    uint32_t tile_it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+      const int nt = t % p.tiles_n, mt = (t / p.tiles_n) % p.tiles_m;
+      const int ab = tile_it & 1;
+      mbar_wait(&tfull[ab], (tile_it >> 1) & 1);
+      tc_fence_after();
+      const int row = mt * TBM + lg * 32 + lane;
+      float* crow = p.C + (long long)row * p.ldc;
+      const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + ab * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = nt * BN + c * 32;
+        if (row < p.M && col0 < p.N) {
+          if (p.bias != nullptr && p.epi == EPI_STORE) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (col0 + q < p.N) v[q] += __ldg(p.bias + col0 + q);
+          }
+          if (p.epi == EPI_STORE && vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(crow + col0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              if (col0 + q < p.N) {
+                if (p.epi == EPI_ATOMIC) atomicAdd(crow + col0 + q, v[q]);
+                else crow[col0 + q] = v[q];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[ab]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows,
+                 bool swizzle32b) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SUG_E_UNSUPPORTED; }
+  SUG_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 4 == 0,
+                "TMA operand needs a 16 B aligned base and a row stride that is a multiple of 4 floats (ld=%llu)",
+                (unsigned long long)ld);
+  cuuint64_t gdim[2] = {inner, rows};
+  cuuint64_t gstr[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SUG_E_BADARG; }
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, int grid, cudaStream_t stream) {
+  using Cfg = TcCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    SUG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, args);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+// a: K-major -> [M, K] row-major with stride lda; MN-major -> [K, M] row-major with stride lda (same for b / N).
+int gemm_tc_f32(const float* a, int64_t lda, int a_mn, const float* b, int64_t ldb, int b_mn, const float* bias, float* c,
+                int64_t ldc, int M, int N, int K, cudaStream_t stream) {
+  SUG_CHECK_ARG(M > 0 && N > 0 && K > 0 && a && b && c, "gemm_tc: bad problem M=%d N=%d K=%d", M, N, K);
+  const int BN = (N <= 64) ? 64 : 128;
+  CUtensorMap tmA, tmB;
+  if (!a_mn) SUG_TRY(make_tmap_2d(&tmA, a, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBM));
+  else SUG_TRY(make_tmap_2d(&tmA, a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, TBK, true));
+  if (!b_mn) SUG_TRY(make_tmap_2d(&tmB, b, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)BN));
+  else SUG_TRY(make_tmap_2d(&tmB, b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, TBK, true));
+  TcArgs args;
+  args.C = c; args.bias = bias; args.ldc = ldc; args.M = M; args.N = N; args.K = K;
+  args.tiles_m = cdiv(M, TBM);
+  args.tiles_n = cdiv(N, BN);
+  const int kb_total = cdiv(K, TBK);
+  const long long tiles = (long long)args.tiles_m * args.tiles_n;
+  int splits = 1;
+  if (tiles < num_sms() && kb_total >= 16 && bias == nullptr) {
+    splits = (int)min((long long)(kb_total / 8), (num_sms() + tiles - 1) / tiles);
+    if (splits < 1) splits = 1;
+  }
+  args.kb_per_split = cdiv(kb_total, splits);
+  args.ksplits = cdiv(kb_total, args.kb_per_split);
+  args.epi = args.ksplits > 1 ? EPI_ATOMIC : EPI_STORE;
+  if (args.epi == EPI_ATOMIC) {
+    SUG_CHECK_ARG(bias == nullptr, "gemm_tc: bias with split-K is not supported");
+    SUG_CUDA(cudaMemset2DAsync(c, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
+  }
+  const int grid = (int)min((long long)num_sms(), tiles * args.ksplits);
+  ProfScope ps(KC_GEMM_TC, 2.0 * M * (double)N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N), stream);
+#define SUG_TC(BN_)                                                                     \
+  do {                                                                                  \
+    if (!a_mn && !b_mn) return launch_tc<BN_, false, false>(tmA, tmB, args, grid, stream); \
+    if (!a_mn && b_mn) return launch_tc<BN_, false, true>(tmA, tmB, args, grid, stream);   \
+    if (a_mn && !b_mn) return launch_tc<BN_, true, false>(tmA, tmB, args, grid, stream);   \
+    return launch_tc<BN_, true, true>(tmA, tmB, args, grid, stream);                       \
+  } while (0)
+  if (BN == 64) SUG_TC(64);
+  SUG_TC(128);
+#undef SUG_TC
+}
+
+}  // namespace sug
+
+extern "C" int sug_gemm_tc_f32(const float* a, int64_t lda, int a_mn_major, const float* b, int64_t ldb, int b_mn_major,
+                               const float* bias, float* c, int64_t ldc, int M, int N, int K, sug_stream_t stream) {
+  return sug::gemm_tc_f32(a, lda, a_mn_major, b, ldb, b_mn_major, bias, c, ldc, M, N, K, (cudaStream_t)stream);
+}

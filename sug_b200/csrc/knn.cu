@@ -10,82 +10,9 @@
 //
 // This CUDA-core kernel is the production path for xyz inputs (C = 3).  Wider feature kNN uses
 // the same selection code behind the tcgen05 distance tiles (knn_tc.cu).
-#include "common.cuh"
+#include "knn_select.cuh"
 
 namespace sug {
-
-constexpr int KTM = 128;         // query rows per CTA (one thread each)
-constexpr int KTN = 64;          // candidates per tile
-constexpr int KCC = 32;          // channels per staged candidate chunk
-constexpr int KQLD = KTM + 4;    // padded leading dims (16B aligned rows, conflict-free transposed stores)
-constexpr int KCLD = KTN + 4;
-constexpr int KPEND = 16;        // pending-queue capacity per row
-
-struct TopK {
-  float* topv;  // [k][KTM]
-  int* topi;    // [k][KTM]
-  float* pv;    // [KPEND][KTM]
-  int* pi;      // [KPEND][KTM]
-  int k;
-  float thr;
-  int minpos;
-  int cnt;
-
-  __device__ __forceinline__ void init(int tid) {
-    for (int s = 0; s < k; ++s) {
-      topv[s * KTM + tid] = -INFINITY;
-      topi[s * KTM + tid] = 0;
-    }
-    thr = -INFINITY;
-    minpos = 0;
-    cnt = 0;
-  }
-  // Predicated append; the caller guarantees cnt < KPEND on entry.
-  __device__ __forceinline__ void offer(int tid, float key, int j) {
-    if (key > thr) {
-      pv[cnt * KTM + tid] = key;
-      pi[cnt * KTM + tid] = j;
-      ++cnt;
-    }
-  }
-  __device__ __forceinline__ void drain(int tid) {
-    for (int p = 0; p < cnt; ++p) {
-      float v = pv[p * KTM + tid];
-      if (v > thr) {
-        topv[minpos * KTM + tid] = v;
-        topi[minpos * KTM + tid] = pi[p * KTM + tid];
-        float mn = INFINITY;
-        int mp = 0;
-        for (int s = 0; s < k; ++s) {
-          float t = topv[s * KTM + tid];
-          if (t < mn) { mn = t; mp = s; }
-        }
-        thr = mn;
-        minpos = mp;
-      }
-    }
-    cnt = 0;
-  }
-  // Sort the k survivors, best (largest key) first; ties -> smaller index first.
-  __device__ __forceinline__ void sort_desc(int tid) {
-    for (int s = 0; s < k - 1; ++s) {
-      float bv = topv[s * KTM + tid];
-      int bi = topi[s * KTM + tid];
-      int bp = s;
-      for (int t = s + 1; t < k; ++t) {
-        float v = topv[t * KTM + tid];
-        int i = topi[t * KTM + tid];
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; bp = t; }
-      }
-      if (bp != s) {
-        topv[bp * KTM + tid] = topv[s * KTM + tid];
-        topi[bp * KTM + tid] = topi[s * KTM + tid];
-        topv[s * KTM + tid] = bv;
-        topi[s * KTM + tid] = bi;
-      }
-    }
-  }
-};
 
 __global__ void __launch_bounds__(KTM)
 knn_simt_kernel(const float* __restrict__ x, int C, int N, int k, long long sb, long long sn, long long sc,
@@ -299,17 +226,26 @@ knn_reverse_kernel(const int* __restrict__ idx, int N, int k, int* __restrict__ 
 
 }  // namespace sug
 
+namespace sug {
+bool knn_tc_supported(int C, int k, long long sn, long long sc, const float* x);
+size_t knn_tc_ws_bytes(int B, int N);
+int knn_tc(const float* x, int B, int C, int N, int k, long long ld, int* idx, void* ws, size_t ws_bytes,
+           cudaStream_t stream);
+}  // namespace sug
+
 extern "C" size_t sug_knn_ws_bytes(int B, int C, int N, int k) {
-  (void)B; (void)C; (void)N; (void)k;
-  return 256;
+  (void)C; (void)k;
+  return sug::knn_tc_ws_bytes(B, N);
 }
 
 extern "C" int sug_knn_f32(const float* x, int B, int C, int N, int k, int64_t sb, int64_t sn, int64_t sc,
                            int32_t* idx, void* ws, size_t ws_bytes, sug_stream_t stream) {
-  (void)ws; (void)ws_bytes;
   SUG_CHECK_ARG(x && idx, "knn: null pointer");
   SUG_CHECK_ARG(B > 0 && C > 0 && N > 0, "knn: bad shape B=%d C=%d N=%d", B, C, N);
   SUG_CHECK_ARG(k > 0 && k <= N && k <= 128, "knn: k=%d must satisfy 1 <= k <= min(N=%d, 128)", k, N);
+  // feature inputs: tcgen05 distance tiles; xyz (C = 3) and odd layouts: CUDA cores
+  if (sb == (int64_t)N * sn && sug::knn_tc_supported(C, k, sn, sc, x))
+    return sug::knn_tc(x, B, C, N, k, sn, idx, ws, ws_bytes, (cudaStream_t)stream);
   return sug::knn_simt(x, B, C, N, k, sb, sn, sc, idx, (cudaStream_t)stream);
 }
 

@@ -60,6 +60,8 @@ def knn_cm(x: torch.Tensor, k: int) -> torch.Tensor:
     if x.dtype != torch.float32:
         x = x.float()
     B, C, N = x.shape
+    if C >= 16:  # feature inputs take the tensor-core path, which wants one row per point
+        return knn_pm(x.transpose(1, 2).contiguous(), k)
     if x.stride(2) != 1:
         x = x.contiguous()
     idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
@@ -74,14 +76,17 @@ def knn_pm(x: torch.Tensor, k: int) -> torch.Tensor:
     """x [B,N,C] point-major -> int32 [B,N,k]."""
     _need_cuda(x)
     x = x.detach()
+    if x.dtype != torch.float32:
+        x = x.float()
     B, N, C = x.shape
-    if x.stride(2) != 1:
+    if x.stride(2) != 1 or x.stride(0) != N * x.stride(1):
         x = x.contiguous()
     idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
     lib = _lib.load()
+    ws = _workspace(lib.sug_knn_ws_bytes(B, C, N, k), x.device)
     with torch.cuda.device(x.device):
-        _lib.check(lib.sug_knn_f32(_ptr(x), B, C, N, k, x.stride(0), x.stride(1), 1, _ptr(idx), None, 0, _stream()),
-                   "sug_knn_f32")
+        _lib.check(lib.sug_knn_f32(_ptr(x), B, C, N, k, x.stride(0), x.stride(1), 1, _ptr(idx), _ptr(ws), ws.numel(),
+                                   _stream()), "sug_knn_f32")
     return idx
 
 
@@ -358,4 +363,27 @@ def gemm(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None) 
     with torch.cuda.device(a.device):
         _lib.check(lib.sug_gemm_f32(_ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), _ptr(bias),
                                     _ptr(c), N, M, N, K, 0, _stream()), "sug_gemm_f32")
+    return c
+
+
+def gemm_tc(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = a @ b.T on the tcgen05 3xTF32 path.  a [M,K] / b [N,K]: either row-major (K-major) or the
+    transpose of a row-major [K,M] / [K,N] tensor (MN-major), detected from the strides."""
+    _need_cuda(a, b)
+    M, K = a.shape
+    N = b.shape[0]
+
+    def major(t):
+        if t.stride(1) == 1:
+            return 0, t.stride(0)
+        if t.stride(0) == 1:
+            return 1, t.stride(1)
+        raise RuntimeError("gemm_tc operands need a unit stride")
+    a_mn, lda = major(a)
+    b_mn, ldb = major(b)
+    c = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        _lib.check(lib.sug_gemm_tc_f32(_ptr(a), lda, a_mn, _ptr(b), ldb, b_mn, _ptr(bias), _ptr(c), N, M, N, K,
+                                       _stream()), "sug_gemm_tc_f32")
     return c
