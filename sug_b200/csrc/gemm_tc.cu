@@ -256,6 +256,13 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t r
   SUG_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 4 == 0,
                 "TMA operand needs a 16 B aligned base and a row stride that is a multiple of 4 floats (ld=%llu)",
                 (unsigned long long)ld);
+  // The encoder is a driver-API call: it needs the primary context bound to THIS thread, which a
+  // fresh autograd worker thread does not have until its first runtime call.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    SUG_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   cuuint64_t gdim[2] = {inner, rows};
   cuuint64_t gstr[1] = {ld * sizeof(float)};
   cuuint32_t box[2] = {32, box_rows};

@@ -14,6 +14,11 @@
 
 namespace sug {
 
+constexpr int KTN = 64;          // candidates per tile
+constexpr int KCC = 32;          // channels per staged candidate chunk
+constexpr int KQLD = KTM + 4;    // padded leading dims (16B aligned rows, conflict-free transposed stores)
+constexpr int KCLD = KTN + 4;
+
 __global__ void __launch_bounds__(KTM)
 knn_simt_kernel(const float* __restrict__ x, int C, int N, int k, long long sb, long long sn, long long sc,
                 int* __restrict__ idx_out) {
@@ -22,11 +27,7 @@ knn_simt_kernel(const float* __restrict__ x, int C, int N, int k, long long sb, 
   float* Cs = Qs + (size_t)C * KQLD;         // [KCC][KCLD] candidate chunk
   float* xxc = Cs + KCC * KCLD;              // [KTN]       |x_j|^2 of the current tile
   TopK tk;
-  tk.topv = xxc + KTN;
-  tk.topi = reinterpret_cast<int*>(tk.topv + (size_t)k * KTM);
-  tk.pv = reinterpret_cast<float*>(tk.topi + (size_t)k * KTM);
-  tk.pi = reinterpret_cast<int*>(tk.pv + KPEND * KTM);
-  tk.k = k;
+  tk.bind(xxc + KTN, k);
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -101,21 +102,18 @@ knn_simt_kernel(const float* __restrict__ x, int C, int N, int k, long long sb, 
     if (tid < KTN) xxc[tid] = xx_part;
     __syncthreads();
 
-    // ---- selection over this tile's 64 keys, 8 at a time --------------------------------------
+    // ---- selection over this tile's 64 keys, 32 at a time -------------------------------------
 #pragma unroll
-    for (int g = 0; g < KTN / 8; ++g) {
-      if (__any_sync(0xffffffffu, tk.cnt > KPEND - 8)) tk.drain(tid);
+    for (int h = 0; h < KTN / 32; ++h) {
+      float keys[32];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int j = g * 8 + u;
-        const int gj = col0 + j;
-        float key = fmaf(2.f, acc[j], -xxq) - xxc[j];
-        if (gj >= N) key = -INFINITY;
-        tk.offer(tid, key, gj);
-      }
+      for (int q = 0; q < 32; ++q) keys[q] = fmaf(2.f, acc[h * 32 + q], -xxq) - xxc[h * 32 + q];
+      const int base = col0 + h * 32;
+      const int nvalid = N - base;
+      const uint32_t valid = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+      tk.consider32(tid, keys, valid, base);
     }
   }
-  tk.drain(tid);
   tk.sort_desc(tid);
   __syncthreads();
 
@@ -124,12 +122,12 @@ knn_simt_kernel(const float* __restrict__ x, int C, int N, int k, long long sb, 
   int* out = idx_out + ((long long)b * N + row0) * k;
   for (int e = tid; e < rows * k; e += KTM) {
     int r = e / k, s = e % k;
-    out[e] = tk.topi[s * KTM + r];
+    out[e] = tk.hi[s * KTM + r];
   }
 }
 
 static size_t knn_simt_smem(int C, int k) {
-  return sizeof(float) * ((size_t)C * KQLD + KCC * KCLD + KTN + 2 * (size_t)k * KTM + 2 * KPEND * KTM);
+  return sizeof(float) * ((size_t)C * KQLD + KCC * KCLD + KTN + TopK::smem_floats(k));
 }
 
 int knn_simt(const float* x, int B, int C, int N, int k, long long sb, long long sn, long long sc, int* idx,

@@ -1,81 +1,96 @@
-// Per-row top-k selection state shared by the CUDA-core (knn.cu) and tcgen05 (knn_tc.cu) kNN kernels.
+// Per-row top-k selection shared by the CUDA-core (knn.cu) and tcgen05 (knn_tc.cu) kNN kernels.
+//
+// One thread owns one query row.  The k best keys seen so far live in a binary MIN-heap in shared
+// memory (column-major [slot][row] so a warp's accesses are conflict-free); the root is the row's
+// current k-th best and doubles as the admission threshold.  Candidates arrive in register chunks
+// of 32: a branch-free pass builds a bitmask of the keys that beat the threshold and stashes the
+// chunk to shared memory; only set bits are then visited (a replace-root + sift-down, <= 4 levels
+// for k = 20), so the cost per candidate is ~5 instructions plus ~60 per accepted candidate, and an
+// accepted candidate tightens the threshold immediately.
 #pragma once
 #include "common.cuh"
 
 namespace sug {
 
-constexpr int KTM = 128;         // query rows per CTA (one thread each)
-constexpr int KTN = 64;          // candidates per tile
-constexpr int KCC = 32;          // channels per staged candidate chunk
-constexpr int KQLD = KTM + 4;    // padded leading dims (16B aligned rows, conflict-free transposed stores)
-constexpr int KCLD = KTN + 4;
-constexpr int KPEND = 16;        // pending-queue capacity per row
+constexpr int KTM = 128;  // query rows per selection group (one thread each)
 
 struct TopK {
-  float* topv;  // [k][KTM]
-  int* topi;    // [k][KTM]
-  float* pv;    // [KPEND][KTM]
-  int* pi;      // [KPEND][KTM]
+  float* hv;     // [k][KTM]  heap values
+  int* hi;       // [k][KTM]  heap payload (candidate index)
+  float* stash;  // [32][KTM] the chunk being examined
   int k;
-  float thr;
-  int minpos;
-  int cnt;
+  float thr;     // == hv[0]: k-th best so far
 
+  static __host__ __device__ size_t smem_floats(int k) { return 2 * (size_t)k * KTM + 32 * KTM; }
+
+  __device__ __forceinline__ void bind(float* base, int k_) {
+    k = k_;
+    hv = base;
+    hi = reinterpret_cast<int*>(base + (size_t)k_ * KTM);
+    stash = base + 2 * (size_t)k_ * KTM;
+  }
   __device__ __forceinline__ void init(int tid) {
     for (int s = 0; s < k; ++s) {
-      topv[s * KTM + tid] = -INFINITY;
-      topi[s * KTM + tid] = 0;
+      hv[s * KTM + tid] = -INFINITY;
+      hi[s * KTM + tid] = 0;
     }
     thr = -INFINITY;
-    minpos = 0;
-    cnt = 0;
   }
-  // Predicated append; the caller guarantees cnt < KPEND on entry.
-  __device__ __forceinline__ void offer(int tid, float key, int j) {
-    if (key > thr) {
-      pv[cnt * KTM + tid] = key;
-      pi[cnt * KTM + tid] = j;
-      ++cnt;
+  // key > thr: replace the root and restore the heap
+  __device__ __forceinline__ void insert(int tid, float key, int j) {
+    int pos = 0;
+    while (true) {
+      const int l = 2 * pos + 1;
+      if (l >= k) break;
+      const int r = l + 1;
+      const float vl = hv[l * KTM + tid];
+      const float vr = r < k ? hv[r * KTM + tid] : INFINITY;
+      const int c = vr < vl ? r : l;
+      const float vc = fminf(vl, vr);
+      if (!(vc < key)) break;
+      hv[pos * KTM + tid] = vc;
+      hi[pos * KTM + tid] = hi[c * KTM + tid];
+      pos = c;
     }
+    hv[pos * KTM + tid] = key;
+    hi[pos * KTM + tid] = j;
+    thr = hv[tid];
   }
-  __device__ __forceinline__ void drain(int tid) {
-    for (int p = 0; p < cnt; ++p) {
-      float v = pv[p * KTM + tid];
-      if (v > thr) {
-        topv[minpos * KTM + tid] = v;
-        topi[minpos * KTM + tid] = pi[p * KTM + tid];
-        float mn = INFINITY;
-        int mp = 0;
-        for (int s = 0; s < k; ++s) {
-          float t = topv[s * KTM + tid];
-          if (t < mn) { mn = t; mp = s; }
-        }
-        thr = mn;
-        minpos = mp;
-      }
+  // keys[0..31] are candidates base .. base+31; `valid` masks out-of-range columns.
+  __device__ __forceinline__ void consider32(int tid, const float (&keys)[32], uint32_t valid, int base) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      if (keys[q] > thr) mask |= 1u << q;
+      stash[q * KTM + tid] = keys[q];
     }
-    cnt = 0;
+    mask &= valid;
+    while (mask) {
+      const int q = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float key = stash[q * KTM + tid];
+      if (key > thr) insert(tid, key, base + q);
+    }
   }
   // Sort the k survivors, best (largest key) first; ties -> smaller index first.
   __device__ __forceinline__ void sort_desc(int tid) {
     for (int s = 0; s < k - 1; ++s) {
-      float bv = topv[s * KTM + tid];
-      int bi = topi[s * KTM + tid];
+      float bv = hv[s * KTM + tid];
+      int bi = hi[s * KTM + tid];
       int bp = s;
       for (int t = s + 1; t < k; ++t) {
-        float v = topv[t * KTM + tid];
-        int i = topi[t * KTM + tid];
+        float v = hv[t * KTM + tid];
+        int i = hi[t * KTM + tid];
         if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; bp = t; }
       }
       if (bp != s) {
-        topv[bp * KTM + tid] = topv[s * KTM + tid];
-        topi[bp * KTM + tid] = topi[s * KTM + tid];
-        topv[s * KTM + tid] = bv;
-        topi[s * KTM + tid] = bi;
+        hv[bp * KTM + tid] = hv[s * KTM + tid];
+        hi[bp * KTM + tid] = hi[s * KTM + tid];
+        hv[s * KTM + tid] = bv;
+        hi[s * KTM + tid] = bi;
       }
     }
   }
 };
-
 
 }  // namespace sug

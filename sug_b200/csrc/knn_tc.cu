@@ -19,7 +19,7 @@ using namespace tc;
 constexpr int QBN = 128;                   // candidates per tile (UMMA N)
 constexpr int QTILE_BYTES = 128 * 32 * 4;  // one [128 x 32] fp32 operand block
 constexpr int QSTAGE_BYTES = 4 * QTILE_BYTES;  // A hi/lo + B hi/lo
-constexpr int QSTAGES = 2;
+constexpr int QSTAGES = 1;  // two CTAs share an SM (8 selection warps); TMEM is double buffered
 constexpr int QTHREADS = 320;
 
 __global__ void row_sqnorm_kernel(const float* __restrict__ x, long long ld, long long P, int C, float* __restrict__ xx) {
@@ -43,7 +43,7 @@ struct KnnTcArgs {
   int mtiles_per_cloud, ntiles;
 };
 
-__global__ void __launch_bounds__(QTHREADS, 1)
+__global__ void __launch_bounds__(QTHREADS, 2)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
   constexpr int S = QSTAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -164,11 +164,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
     const int et = threadIdx.x - 192;  // 0..127, used for cooperative loads
     const int r = lg * 32 + lane;      // query row inside the block == TMEM lane
     TopK tk;
-    tk.k = p.k;
-    tk.topv = sel;
-    tk.topi = reinterpret_cast<int*>(tk.topv + (size_t)p.k * KTM);
-    tk.pv = reinterpret_cast<float*>(tk.topi + (size_t)p.k * KTM);
-    tk.pi = reinterpret_cast<int*>(tk.pv + KPEND * KTM);
+    tk.bind(sel, p.k);
     uint32_t tile_it = 0;
     for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x) {
       const int b = mt / p.mtiles_per_cloud, r0 = (mt % p.mtiles_per_cloud) * 128;
@@ -190,27 +186,27 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + ab * QBN + c * 32, v);
           tmem_ld_wait();
+          const float4* xj = reinterpret_cast<const float4*>(xxs + ab * QBN + c * 32);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (__any_sync(0xffffffffu, tk.cnt > KPEND - 8)) tk.drain(r);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int q = g * 8 + u;
-              const int gj = nt * QBN + c * 32 + q;
-              float key = fmaf(2.f, v[q], -xxq) - xxs[ab * QBN + c * 32 + q];
-              if (gj >= p.N) key = -INFINITY;
-              tk.offer(r, key, gj);
-            }
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 n4 = xj[q4];
+            v[4 * q4 + 0] = fmaf(2.f, v[4 * q4 + 0], -xxq) - n4.x;
+            v[4 * q4 + 1] = fmaf(2.f, v[4 * q4 + 1], -xxq) - n4.y;
+            v[4 * q4 + 2] = fmaf(2.f, v[4 * q4 + 2], -xxq) - n4.z;
+            v[4 * q4 + 3] = fmaf(2.f, v[4 * q4 + 3], -xxq) - n4.w;
           }
+          const int base = nt * QBN + c * 32;
+          const int nvalid = p.N - base;
+          const uint32_t valid = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+          tk.consider32(r, v, valid, base);
         }
         tc_fence_before();
         mbar_arrive(&tempty[ab]);
       }
-      tk.drain(r);
       tk.sort_desc(r);
       if (row < p.N) {
         int* o = p.idx + (cbase + row) * p.k;
-        for (int s = 0; s < p.k; ++s) o[s] = tk.topi[s * KTM + r];
+        for (int s = 0; s < p.k; ++s) o[s] = tk.hi[s * KTM + r];
       }
     }
   }
@@ -224,7 +220,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
 }
 
 static size_t knn_tc_smem(int k) {
-  return (size_t)QSTAGES * QSTAGE_BYTES + 1024 + 256 + sizeof(float) * (2 * QBN + 2 * (size_t)k * KTM + 2 * KPEND * KTM);
+  return (size_t)QSTAGES * QSTAGE_BYTES + 1024 + 256 + sizeof(float) * (2 * QBN + TopK::smem_floats(k));
 }
 
 bool knn_tc_supported(int C, int k, long long sn, long long sc, const float* x) {
@@ -257,7 +253,7 @@ int knn_tc(const float* x, int B, int C, int N, int k, long long ld, int* idx, v
     SUG_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const int grid = min(num_sms(), B * a.mtiles_per_cloud);
+  const int grid = min(2 * num_sms(), B * a.mtiles_per_cloud);
   ProfScope ps(KC_KNN_TC, 2.0 * B * (double)N * N * C, 4.0 * B * (double)N * (C + k), stream);
   knn_tc_kernel<<<grid, QTHREADS, smem, stream>>>(tmX, a);
   SUG_LAUNCH_CHECK();

@@ -536,20 +536,24 @@ def test_sug_step_golden(S, golden):
     assert_close(r["pred_t1"], g["pred_t1"], 1e-3, "pred_t1")
     params = dict(net.named_parameters())
     assert_close(r["loss"], ro["loss"], 1e-3, "loss vs oracle")
-    worst, worst_fix = ("", 0.0), ("", 0.0)
-    n = 0
+    # A gradient that is mathematically zero (e.g. g.conv1d.bias: a per-channel constant in front
+    # of train-mode BatchNorm layers) is pure rounding noise on both sides, so the error of every
+    # parameter is measured against max(|g_ref|, 1e-4 * largest gradient norm of the model).
+    gmax = max(float(v.grad.norm()) for v in sd.values() if v.grad is not None)
+    rows, n = [], 0
     for k, p in params.items():
         go = sd[k].grad
         if go is None:
             assert p.grad is None, f"{k} has a gradient here but not in the reference"
             continue
-        e = relerr(p.grad, go)
-        worst = max(worst, (k, e), key=lambda t: t[1])
+        d = float((p.grad.detach().cpu().double() - go.double()).norm())
+        rows.append((d / max(float(go.norm()), 1e-4 * gmax), k, float(go.norm())))
         n += 1
-        if "gf." + k in g:
-            worst_fix = max(worst_fix, (k, relerr(p.grad, g["gf." + k])), key=lambda t: t[1])
-    print(f"{n} parameter gradients; worst rel err vs oracle(fp64 MMD): {worst}; vs fp32 reference fixture: {worst_fix}")
-    assert worst[1] < 2e-3, f"gradient of {worst[0]}: rel err {worst[1]:.2e}"
+    rows.sort(reverse=True)
+    print(f"{n} parameter gradients vs oracle (fp64 MMD); five worst (err, name, |g_ref|): {rows[:5]}")
+    fix = sorted(((relerr(params[k[3:]].grad, v), k[3:]) for k, v in g.items() if k.startswith("gf.")), reverse=True)
+    print(f"vs the fp32 reference fixture (MMD-noise contaminated): {fix[:3]}")
+    assert rows[0][0] < 2e-3, f"gradient of {rows[0][1]}: rel err {rows[0][0]:.2e}"
     assert n >= 50
     assert params["g.input_transform_net.fc3.weight"].grad is None
     assert params["g.node_fea_adapt.trans.conv.0.weight"].grad is None
