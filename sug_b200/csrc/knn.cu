@@ -10,6 +10,8 @@
 //
 // This CUDA-core kernel is the production path for xyz inputs (C = 3).  Wider feature kNN uses
 // the same selection code behind the tcgen05 distance tiles (knn_tc.cu).
+#include <type_traits>
+
 #include "knn_select.cuh"
 
 namespace sug {
@@ -19,6 +21,8 @@ constexpr int KCC = 32;          // channels per staged candidate chunk
 constexpr int KQLD = KTM + 4;    // padded leading dims (16B aligned rows, conflict-free transposed stores)
 constexpr int KCLD = KTN + 4;
 
+// K > 0: compile-time k with the register-resident sorted list; K == 0: any k, heap in shared memory.
+template <int K>
 __global__ void __launch_bounds__(KTM)
 knn_simt_kernel(const float* __restrict__ x, int C, int N, int k, long long sb, long long sn, long long sc,
                 int* __restrict__ idx_out) {
@@ -26,8 +30,9 @@ knn_simt_kernel(const float* __restrict__ x, int C, int N, int k, long long sb, 
   float* Qs = smem;                          // [C][KQLD]   query tile, channel-major
   float* Cs = Qs + (size_t)C * KQLD;         // [KCC][KCLD] candidate chunk
   float* xxc = Cs + KCC * KCLD;              // [KTN]       |x_j|^2 of the current tile
-  TopK tk;
-  tk.bind(xxc + KTN, k);
+  typename std::conditional<(K > 0), TopKReg<(K > 0 ? K : 1)>, TopK>::type tk;
+  if constexpr (K > 0) tk.bind(xxc + KTN);
+  else tk.bind(xxc + KTN, k);
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -49,7 +54,8 @@ knn_simt_kernel(const float* __restrict__ x, int C, int N, int k, long long sb, 
       Qs[c * KQLD + r] = gr < N ? __ldg(xb + (long long)gr * sn + (long long)c * sc) : 0.f;
     }
   }
-  tk.init(tid);
+  if constexpr (K > 0) tk.init();
+  else tk.init(tid);
   __syncthreads();
   float xxq = 0.f;
   for (int c = 0; c < C; ++c) {
@@ -114,7 +120,15 @@ knn_simt_kernel(const float* __restrict__ x, int C, int N, int k, long long sb, 
       tk.consider32(tid, keys, valid, base);
     }
   }
-  tk.sort_desc(tid);
+  int* ranked = reinterpret_cast<int*>(xxc + KTN);  // [k][KTM] ranked indices for the coalesced write
+  if constexpr (K > 0) {
+    __syncthreads();  // every thread is done with the stash before it is reused
+#pragma unroll
+    for (int s = 0; s < K; ++s) ranked[s * KTM + tid] = tk.id[s];
+  } else {
+    tk.sort_desc(tid);
+    ranked = tk.hi;
+  }
   __syncthreads();
 
   // ---- coalesced write of the tile's [rows][k] block --------------------------------------------
@@ -122,28 +136,37 @@ knn_simt_kernel(const float* __restrict__ x, int C, int N, int k, long long sb, 
   int* out = idx_out + ((long long)b * N + row0) * k;
   for (int e = tid; e < rows * k; e += KTM) {
     int r = e / k, s = e % k;
-    out[e] = tk.hi[s * KTM + r];
+    out[e] = ranked[s * KTM + r];
   }
 }
 
 static size_t knn_simt_smem(int C, int k) {
-  return sizeof(float) * ((size_t)C * KQLD + KCC * KCLD + KTN + TopK::smem_floats(k));
+  const size_t sel = (k == 20 || k == 40) ? (size_t)(k > 32 ? k : 32) * KTM : TopK::smem_floats(k);
+  return sizeof(float) * ((size_t)C * KQLD + KCC * KCLD + KTN + sel);
+}
+
+template <int K>
+static int knn_simt_launch(const float* x, int C, int N, int k, long long sb, long long sn, long long sc, int* idx,
+                           dim3 grid, size_t smem, cudaStream_t stream) {
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SUG_CUDA(cudaFuncSetAttribute(knn_simt_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  knn_simt_kernel<K><<<grid, KTM, smem, stream>>>(x, C, N, k, sb, sn, sc, idx);
+  SUG_LAUNCH_CHECK();
+  return 0;
 }
 
 int knn_simt(const float* x, int B, int C, int N, int k, long long sb, long long sn, long long sc, int* idx,
              cudaStream_t stream) {
   size_t smem = knn_simt_smem(C, k);
   SUG_CHECK_ARG(smem <= 227 * 1024, "knn: C=%d k=%d needs %zu B of shared memory (> 227 KB)", C, k, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    SUG_CUDA(cudaFuncSetAttribute(knn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   dim3 grid(cdiv(N, KTM), B);
   ProfScope ps(KC_KNN, 2.0 * B * (double)N * N * C, 4.0 * B * (double)N * (C + k), stream);
-  knn_simt_kernel<<<grid, KTM, smem, stream>>>(x, C, N, k, sb, sn, sc, idx);
-  SUG_LAUNCH_CHECK();
-  return 0;
+  if (k == 20) return knn_simt_launch<20>(x, C, N, k, sb, sn, sc, idx, grid, smem, stream);
+  if (k == 40) return knn_simt_launch<40>(x, C, N, k, sb, sn, sc, idx, grid, smem, stream);
+  return knn_simt_launch<0>(x, C, N, k, sb, sn, sc, idx, grid, smem, stream);
 }
 
 // ---- transposed graph -------------------------------------------------------------------------

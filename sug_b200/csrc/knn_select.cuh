@@ -93,4 +93,53 @@ struct TopK {
   }
 };
 
+// Register-resident variant for the common k (20, 40): the list is kept SORTED (best first) in
+// registers with fully static indexing, so an accepted candidate costs ~5 ALU instructions per slot
+// (max/min on the keys, one compare + two selects on the payload) with no shared-memory round trips
+// on the dependent chain; the k-th best is v[K-1] and the final list needs no sort.
+template <int K>
+struct TopKReg {
+  float v[K];
+  int id[K];
+  float* stash;  // [32][KTM]
+  float thr;
+
+  static __host__ __device__ size_t smem_floats() { return 32 * KTM; }
+
+  __device__ __forceinline__ void bind(float* base) { stash = base; }
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int s = 0; s < K; ++s) { v[s] = -INFINITY; id[s] = 0; }
+    thr = -INFINITY;
+  }
+  __device__ __forceinline__ void insert(float key, int j) {
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      const bool gt = key > v[s];  // strict: an equal key stays behind the earlier (smaller) index
+      const float hi_ = fmaxf(v[s], key), lo_ = fminf(v[s], key);
+      const int ni = gt ? j : id[s];
+      j = gt ? id[s] : j;
+      v[s] = hi_;
+      key = lo_;
+      id[s] = ni;
+    }
+    thr = v[K - 1];
+  }
+  __device__ __forceinline__ void consider32(int tid, const float (&keys)[32], uint32_t valid, int base) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      if (keys[q] > thr) mask |= 1u << q;
+      stash[q * KTM + tid] = keys[q];
+    }
+    mask &= valid;
+    while (mask) {
+      const int q = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float key = stash[q * KTM + tid];
+      if (key > thr) insert(key, base + q);
+    }
+  }
+};
+
 }  // namespace sug

@@ -9,6 +9,8 @@
 //        D_ij = (-|x_i|^2 + 2 x_i.x_j) - |x_j|^2
 // and run the same pending-queue top-k selection as the CUDA-core kernel while the next tile's MMAs
 // are in flight.  The N x N matrix exists only tile by tile in TMEM.
+#include <type_traits>
+
 #include "knn_select.cuh"
 #include "tc_common.cuh"
 
@@ -43,7 +45,9 @@ struct KnnTcArgs {
   int mtiles_per_cloud, ntiles;
 };
 
-__global__ void __launch_bounds__(QTHREADS, 2)
+// K > 0: compile-time k (register-resident sorted list); K == 0: any k (heap in shared memory).
+template <int K>
+__global__ void __launch_bounds__(QTHREADS, (K == 40 ? 1 : 2))
 knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
   constexpr int S = QSTAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -163,15 +167,17 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
     const int lg = warp & 3;
     const int et = threadIdx.x - 192;  // 0..127, used for cooperative loads
     const int r = lg * 32 + lane;      // query row inside the block == TMEM lane
-    TopK tk;
-    tk.bind(sel, p.k);
+    typename std::conditional<(K > 0), TopKReg<(K > 0 ? K : 1)>, TopK>::type tk;
+    if constexpr (K > 0) tk.bind(sel);
+    else tk.bind(sel, p.k);
     uint32_t tile_it = 0;
     for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x) {
       const int b = mt / p.mtiles_per_cloud, r0 = (mt % p.mtiles_per_cloud) * 128;
       const int row = r0 + r;
       const long long cbase = (long long)b * p.N;
       const float xxq = row < p.N ? __ldg(p.xx + cbase + row) : 0.f;
-      tk.init(r);
+      if constexpr (K > 0) tk.init();
+      else tk.init(r);
       for (int nt = 0; nt < p.ntiles; ++nt, ++tile_it) {
         const int ab = tile_it & 1;
         {
@@ -203,10 +209,18 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
         tc_fence_before();
         mbar_arrive(&tempty[ab]);
       }
-      tk.sort_desc(r);
-      if (row < p.N) {
-        int* o = p.idx + (cbase + row) * p.k;
-        for (int s = 0; s < p.k; ++s) o[s] = tk.hi[s * KTM + r];
+      if constexpr (K > 0) {
+        if (row < p.N) {
+          int* o = p.idx + (cbase + row) * K;
+#pragma unroll
+          for (int s = 0; s < K; ++s) o[s] = tk.id[s];
+        }
+      } else {
+        tk.sort_desc(r);
+        if (row < p.N) {
+          int* o = p.idx + (cbase + row) * p.k;
+          for (int s = 0; s < p.k; ++s) o[s] = tk.hi[s * KTM + r];
+        }
       }
     }
   }
@@ -220,7 +234,20 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
 }
 
 static size_t knn_tc_smem(int k) {
-  return (size_t)QSTAGES * QSTAGE_BYTES + 1024 + 256 + sizeof(float) * (2 * QBN + TopK::smem_floats(k));
+  const size_t sel = (k == 20 || k == 40) ? 32 * KTM : TopK::smem_floats(k);
+  return (size_t)QSTAGES * QSTAGE_BYTES + 1024 + 256 + sizeof(float) * (2 * QBN + sel);
+}
+
+template <int K>
+static int knn_tc_launch(const CUtensorMap& tmX, const KnnTcArgs& a, int grid, size_t smem, cudaStream_t stream) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    SUG_CUDA(cudaFuncSetAttribute(knn_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  knn_tc_kernel<K><<<grid, QTHREADS, smem, stream>>>(tmX, a);
+  SUG_LAUNCH_CHECK();
+  return 0;
 }
 
 bool knn_tc_supported(int C, int k, long long sn, long long sc, const float* x) {
@@ -248,16 +275,11 @@ int knn_tc(const float* x, int B, int C, int N, int k, long long ld, int* idx, v
   a.mtiles_per_cloud = cdiv(N, 128);
   a.ntiles = cdiv(N, QBN);
   const size_t smem = knn_tc_smem(k);
-  static size_t configured = 0;
-  if (smem > configured) {
-    SUG_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  const int grid = min(2 * num_sms(), B * a.mtiles_per_cloud);
+  const int grid = min((k == 40 ? 1 : 2) * num_sms(), B * a.mtiles_per_cloud);
   ProfScope ps(KC_KNN_TC, 2.0 * B * (double)N * N * C, 4.0 * B * (double)N * (C + k), stream);
-  knn_tc_kernel<<<grid, QTHREADS, smem, stream>>>(tmX, a);
-  SUG_LAUNCH_CHECK();
-  return 0;
+  if (k == 20) return knn_tc_launch<20>(tmX, a, grid, smem, stream);
+  if (k == 40) return knn_tc_launch<40>(tmX, a, grid, smem, stream);
+  return knn_tc_launch<0>(tmX, a, grid, smem, stream);
 }
 
 }  // namespace sug
