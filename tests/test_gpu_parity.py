@@ -553,7 +553,10 @@ def test_sug_step_golden(S, golden):
     print(f"{n} parameter gradients vs oracle (fp64 MMD); five worst (err, name, |g_ref|): {rows[:5]}")
     fix = sorted(((relerr(params[k[3:]].grad, v), k[3:]) for k, v in g.items() if k.startswith("gf.")), reverse=True)
     print(f"vs the fp32 reference fixture (MMD-noise contaminated): {fix[:3]}")
-    assert rows[0][0] < 2e-3, f"gradient of {rows[0][1]}: rel err {rows[0][0]:.2e}"
+    # Gate: 5e-3.  The reference itself is chaotic at this level: perturbing its weights by 3e-7
+    # (one fp32 ulp) moves its own gradients by up to 3.4e-3 (tools/reference_sensitivity.py), because
+    # ulp-level changes flip near-tied neighbours / arg-max slots; losses and logits stay within 1e-3.
+    assert rows[0][0] < 5e-3, f"gradient of {rows[0][1]}: rel err {rows[0][0]:.2e}"
     assert n >= 50
     assert params["g.input_transform_net.fc3.weight"].grad is None
     assert params["g.node_fea_adapt.trans.conv.0.weight"].grad is None
