@@ -108,6 +108,24 @@ int sug_mlp_pool_bwd(const float* gout, const float* x, int64_t ldx, const float
                      sug_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * conv_2d over points without pooling: Conv2d(1x1)(+bias) -> BatchNorm2d -> ReLU / LeakyReLU
+ *                                                        reference: model/model_utils.py:8-32
+ * (adapt_layer_off.residual, PointNet conv1..conv4, T-Net conv2d1/2).  x [P, Cin] point-major,
+ * y [P, Cout] keeps the linear output for the backward (which overwrites it with dL/dy),
+ * out [P, Cout] with row stride ldo.
+ * ------------------------------------------------------------------------------------------- */
+int sug_linear_bn_act_fwd(const float* x, int64_t ldx, const float* w, const float* bias,
+                          const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, int64_t P, int Cin, int Cout, float eps, float momentum,
+                          float slope, int training, float* y, float* out, int64_t ldo,
+                          float* save_mean_invstd, void* ws, size_t ws_bytes, sug_stream_t stream);
+int sug_linear_bn_act_bwd(const float* gout, int64_t ldg, const float* x, int64_t ldx, const float* w,
+                          const float* gamma, const float* beta, float* y,
+                          const float* save_mean_invstd, int64_t P, int Cin, int Cout, float slope,
+                          float* dx, int64_t lddx, float* dw, float* dbias, float* dgamma,
+                          float* dbeta, void* ws, size_t ws_bytes, sug_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * mix_rbf_mmd2(X, Y, sigma_list, biased=True, sample_weights=w)    reference: model/mmd.py:239-312
  * z [2m, D] = cat(X, Y) with row stride ldz.  weights [m] or NULL (column weights of K_XY,
  * mmd.py:293-297).  Squared norms are taken from the Gram diagonal exactly like mmd.py:245-247.
@@ -154,6 +172,13 @@ int sug_three_nn(const float* xyz, const float* nodes, int B, int N, int M, int 
 int sug_gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
                  const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
                  sug_stream_t stream);
+
+/* sug_gemm_f32's problem statement routed through the library's dispatcher: tcgen05 3xTF32 when the
+ * operands satisfy the TMA constraints, the exact CUDA-core kernel otherwise.  Used by the host
+ * layer for the bias-only linear layers (Conv1d(128,64,1), Model.py:70,101). */
+int sug_gemm_auto_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
+                      const float* bias, float* c, int64_t ldc, int M, int N, int K,
+                      sug_stream_t stream);
 
 /* fp32-accurate tensor-core GEMM (tcgen05 kind::tf32, 3-term hi/lo split, TMA-fed, TMEM
  * accumulators): C[M,N] = A * B^T (+ bias).  a_mn_major == 0: a is [M,K] row-major (stride lda);

@@ -30,8 +30,15 @@ class CALayer(nn.Module):
         self.bn = nn.BatchNorm1d(4096)
 
     def forward(self, x):
-        with exact_conv():
-            y = self.conv_du(x)
+        if x.is_cuda:
+            # the two 1x1 convolutions on a [B,C,1,1] tensor are plain linear layers; cuBLAS fp32
+            # instead of cuDNN's (TF32-by-default, slow weight-gradient) convolution kernels
+            c0, c2 = self.conv_du[0], self.conv_du[2]
+            v = x.reshape(x.shape[0], -1)
+            y = F.relu(F.linear(v, c0.weight.view(c0.out_channels, -1), c0.bias))
+            y = torch.sigmoid(F.linear(y, c2.weight.view(c2.out_channels, -1), c2.bias))
+            return self.bn(v * y + v)
+        y = self.conv_du(x)
         y = x * y + x
         y = y.view(y.shape[0], -1)
         return self.bn(y)
@@ -74,9 +81,9 @@ class DGCNN(nn.Module):
         x0 = x_loc.transpose(1, 2).contiguous()  # point-major [B,N,3]
         x1 = self.conv1.edgeconv(x0, ops.knn_cm(x_loc, k))
         x2 = self.conv2.edgeconv(x1, ops.knn_pm(x1, k))
-        x_, node_fea, node_off = self.node_fea_adapt(x2.transpose(1, 2).unsqueeze(3), x_loc)  # [B,64,N,1]
-        with exact_conv():
-            x2 = self.conv1d(x_.squeeze(-1)).transpose(1, 2).contiguous()
+        x_, node_pm, _ = self.node_fea_adapt.forward_pm(x2, x_loc)           # [B,N,128], [B,64 nodes,64]
+        node_fea = node_pm.transpose(1, 2).unsqueeze(3)                       # reference layout [B,64,64,1]
+        x2 = ops.linear(x_, self.conv1d.weight, self.conv1d.bias)             # Conv1d(128,64,1) on point-major rows
         x3 = self.conv3.edgeconv(x2, ops.knn_pm(x2, k))
         x4 = self.conv4.edgeconv(x3, ops.knn_pm(x3, k))
         feat = self._tail(torch.cat((x1, x2, x3, x4), dim=2))

@@ -40,6 +40,9 @@ SIGNATURES = {
     "sug_knn_query": (I, [P, P, I, I, I, I, P, P]),
     "sug_three_nn": (I, [P, P, I, I, I, I, P, P]),
     "sug_gemm_f32": (I, [P, L, L, P, L, L, P, P, L, I, I, I, I, P]),
+    "sug_gemm_auto_f32": (I, [P, L, L, P, L, L, P, P, L, I, I, I, P]),
+    "sug_linear_bn_act_fwd": (I, [P, L, P, P, P, P, P, P, L, I, I, F, F, F, I, P, P, L, P, P, Z, P]),
+    "sug_linear_bn_act_bwd": (I, [P, L, P, L, P, P, P, P, P, L, I, I, F, P, L, P, P, P, P, P, Z, P]),
     "sug_gemm_tc_f32": (I, [P, L, I, P, L, I, P, P, L, I, I, I, P]),
     "sug_prof_num_classes": (I, []),
     "sug_prof_class_name": (c_char_p, [I]),

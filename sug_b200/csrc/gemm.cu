@@ -160,6 +160,12 @@ int gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t s
 
 }  // namespace sug
 
+// Same problem statement as sug_gemm_f32 but through the dispatcher (tensor cores when possible).
+extern "C" int sug_gemm_auto_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
+                                 const float* bias, float* c, int64_t ldc, int M, int N, int K, sug_stream_t stream) {
+  return sug::gemm_f32(a, sam, sak, b, sbn, sbk, bias, c, ldc, M, N, K, 0, (cudaStream_t)stream);
+}
+
 extern "C" int sug_gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
                             const float* bias, float* c, int64_t ldc, int M, int N, int K, int accumulate,
                             sug_stream_t stream) {

@@ -238,9 +238,185 @@ pool_bwd_main_kernel(float* __restrict__ y, const float* __restrict__ gout, cons
   }
 }
 
+// ---- pointwise (no pooling) BatchNorm + activation backward ----------------------------------------
+// dz = g * act'(z);  G1 += dz;  G2 += dz * yhat      (y = linear output, z = scale*y + shift)
+__global__ void __launch_bounds__(256)
+pw_bwd_pre_kernel(const float* __restrict__ y, const float* __restrict__ gout, long long ldg,
+                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                  const float* __restrict__ mean_invstd, long long P, int Cout, float slope,
+                  double* __restrict__ gsums) {
+  __shared__ double red[256][8];
+  const int tid = threadIdx.x;
+  const int c4l = tid % PCQ, rl = tid / PCQ;
+  const int c4 = blockIdx.x * PCQ + c4l;
+  const bool active = 4 * c4 < Cout;
+  double g1[4] = {0, 0, 0, 0}, g2[4] = {0, 0, 0, 0};
+  if (active) {
+    float sc[4], sh[4], mean[4], is[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int c = 4 * c4 + u;
+      mean[u] = __ldg(mean_invstd + c);
+      is[u] = __ldg(mean_invstd + Cout + c);
+      sc[u] = __ldg(gamma + c) * is[u];
+      sh[u] = __ldg(beta + c) - mean[u] * sc[u];
+    }
+    float f1[4] = {0, 0, 0, 0}, f2[4] = {0, 0, 0, 0};
+    int run = 0;
+    for (long long r = (long long)blockIdx.y * PRL + rl; r < P; r += (long long)gridDim.y * PRL) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(y + r * Cout) + c4);
+      float4 g = __ldg(reinterpret_cast<const float4*>(gout + r * ldg) + c4);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float dz = gg[u] * act_leaky_grad(fmaf(sc[u], vv[u], sh[u]), slope);
+        f1[u] += dz;
+        f2[u] = fmaf(dz, (vv[u] - mean[u]) * is[u], f2[u]);
+      }
+      if (++run == 32) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { g1[u] += (double)f1[u]; g2[u] += (double)f2[u]; f1[u] = 0.f; f2[u] = 0.f; }
+        run = 0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { g1[u] += (double)f1[u]; g2[u] += (double)f2[u]; }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { red[tid][u] = g1[u]; red[tid][4 + u] = g2[u]; }
+  __syncthreads();
+  if (active && rl == 0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double a = 0, q = 0;
+      for (int r = 0; r < PRL; ++r) { a += red[r * PCQ + c4l][u]; q += red[r * PCQ + c4l][4 + u]; }
+      atomicAdd(&gsums[4 * c4 + u], a);
+      atomicAdd(&gsums[Cout + 4 * c4 + u], q);
+    }
+  }
+}
+
+// y <- dL/dy = scale (dz - G1/M - yhat G2/M), in place
+__global__ void __launch_bounds__(256)
+pw_bwd_main_kernel(float* __restrict__ y, const float* __restrict__ gout, long long ldg,
+                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ mean_invstd, const double* __restrict__ gsums, long long P, int Cout,
+                   float slope, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int tid = threadIdx.x;
+  const int c4l = tid % PCQ, rl = tid / PCQ;
+  const int c4 = blockIdx.x * PCQ + c4l;
+  if (4 * c4 >= Cout) return;
+  const double Md = (double)P;
+  float sc[4], sh[4], mean[4], is[4], c1[4], c2[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    int c = 4 * c4 + u;
+    mean[u] = __ldg(mean_invstd + c);
+    is[u] = __ldg(mean_invstd + Cout + c);
+    sc[u] = __ldg(gamma + c) * is[u];
+    sh[u] = __ldg(beta + c) - mean[u] * sc[u];
+    double G1 = gsums[c], G2 = gsums[Cout + c];
+    c1[u] = (float)(G1 / Md);
+    c2[u] = (float)(G2 / Md);
+    if (blockIdx.y == 0 && rl == 0) { dbeta[c] = (float)G1; dgamma[c] = (float)G2; }
+  }
+  for (long long r = (long long)blockIdx.y * PRL + rl; r < P; r += (long long)gridDim.y * PRL) {
+    float4* p = reinterpret_cast<float4*>(y + r * Cout) + c4;
+    float4 v = *p;
+    float4 g = __ldg(reinterpret_cast<const float4*>(gout + r * ldg) + c4);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    const float gg[4] = {g.x, g.y, g.z, g.w};
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float dz = gg[u] * act_leaky_grad(fmaf(sc[u], vv[u], sh[u]), slope);
+      o[u] = sc[u] * (dz - c1[u] - (vv[u] - mean[u]) * is[u] * c2[u]);
+    }
+    *p = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// defined in edgeconv.cu
+__global__ void bn_act_kernel(const float* __restrict__ ext, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, const float* __restrict__ mean_invstd, long long P,
+                              int Cout, float slope, float* __restrict__ out, long long ldo);
+
 }  // namespace sug
 
 using namespace sug;
+
+// ---- linear (1x1 conv over points) + BatchNorm + activation --------------------------------------
+extern "C" int sug_linear_bn_act_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var, int64_t P, int Cin,
+                                     int Cout, float eps, float momentum, float slope, int training, float* y,
+                                     float* out, int64_t ldo, float* save_mean_invstd, void* ws, size_t ws_bytes,
+                                     sug_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SUG_CHECK_ARG(x && w && gamma && beta && running_mean && running_var && y && out, "linear_bn_act_fwd: null pointer");
+  SUG_CHECK_ARG(P > 0 && Cin > 0 && Cout > 0 && Cout % 4 == 0 && ldo % 4 == 0, "linear_bn_act_fwd: bad shape");
+  Workspace W(ws, ws_bytes);
+  double* sums = W.take<double>(2 * (size_t)Cout);
+  float* mi_eval = W.take<float>(2 * (size_t)Cout);
+  if (!W.ok()) { set_error("linear_bn_act_fwd: workspace too small"); return SUG_E_WORKSPACE; }
+  SUG_TRY(gemm_f32(x, ldx, 1, w, Cin, 1, bias, y, Cout, (int)P, Cout, Cin, 0, stream));
+  const int gx = cdiv(Cout, PCQ * 4);
+  const float* mi = save_mean_invstd;
+  if (training) {
+    SUG_CHECK_ARG(save_mean_invstd != nullptr, "linear_bn_act_fwd: training needs save_mean_invstd");
+    SUG_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cout, stream));
+    int gy = (int)min((long long)num_sms() * 4 / gx + 1, (long long)(P + PRL - 1) / PRL);
+    {
+      ProfScope ps(KC_COLSTATS, 3.0 * P * Cout, 4.0 * P * Cout, stream);
+      col_stats_kernel<<<dim3(gx, gy), 256, 0, stream>>>(y, P, Cout, sums);
+    }
+    SUG_LAUNCH_CHECK();
+    SUG_TRY(bn_finalize_stats(sums, Cout, (double)P, eps, momentum, running_mean, running_var, save_mean_invstd, stream));
+  } else {
+    SUG_TRY(bn_eval_stats(running_mean, running_var, Cout, eps, mi_eval, stream));
+    mi = mi_eval;
+  }
+  long long total = P * (Cout >> 2);
+  int g2 = (int)min((long long)num_sms() * 8, (total + 255) / 256);
+  {
+    ProfScope ps(KC_BN_ACT, 2.0 * P * Cout, 8.0 * P * Cout, stream);
+    bn_act_kernel<<<g2, 256, 2 * Cout * sizeof(float), stream>>>(y, gamma, beta, mi, P, Cout, slope, out, ldo);
+  }
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_linear_bn_act_bwd(const float* gout, int64_t ldg, const float* x, int64_t ldx, const float* w,
+                                     const float* gamma, const float* beta, float* y, const float* save_mean_invstd,
+                                     int64_t P, int Cin, int Cout, float slope, float* dx, int64_t lddx, float* dw,
+                                     float* dbias, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+                                     sug_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SUG_CHECK_ARG(gout && x && w && gamma && beta && y && save_mean_invstd && dw && dgamma && dbeta,
+                "linear_bn_act_bwd: null pointer");
+  SUG_CHECK_ARG(P > 0 && Cin > 0 && Cout > 0 && Cout % 4 == 0 && ldg % 4 == 0, "linear_bn_act_bwd: bad shape");
+  Workspace W(ws, ws_bytes);
+  double* gsums = W.take<double>(2 * (size_t)Cout);
+  if (!W.ok()) { set_error("linear_bn_act_bwd: workspace too small"); return SUG_E_WORKSPACE; }
+  SUG_CUDA(cudaMemsetAsync(gsums, 0, sizeof(double) * 2 * Cout, stream));
+  const int gx = cdiv(Cout, PCQ * 4);
+  const int gy = (int)min((long long)num_sms() * 4 / gx + 1, (long long)(P + PRL - 1) / PRL);
+  {
+    ProfScope ps(KC_POOL_BWD, 8.0 * P * Cout, 8.0 * P * Cout, stream);
+    pw_bwd_pre_kernel<<<dim3(gx, gy), 256, 0, stream>>>(y, gout, ldg, gamma, beta, save_mean_invstd, P, Cout, slope, gsums);
+  }
+  SUG_LAUNCH_CHECK();
+  {
+    ProfScope ps(KC_POOL_BWD, 10.0 * P * Cout, 12.0 * P * Cout, stream);
+    pw_bwd_main_kernel<<<dim3(gx, gy), 256, 0, stream>>>(y, gout, ldg, gamma, beta, save_mean_invstd, gsums, P, Cout,
+                                                         slope, dgamma, dbeta);
+  }
+  SUG_LAUNCH_CHECK();
+  if (dbias != nullptr) SUG_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, stream));
+  SUG_TRY(gemm_f32(y, 1, Cout, x, 1, ldx, nullptr, dw, Cin, Cout, Cin, (int)P, 0, stream));
+  if (dx != nullptr) SUG_TRY(gemm_f32(y, Cout, 1, w, 1, Cin, nullptr, dx, lddx, (int)P, Cin, Cout, 0, stream));
+  return 0;
+}
 
 extern "C" size_t sug_mlp_pool_ws_bytes(int B, int N, int Cin, int Cout) {
   (void)B; (void)N; (void)Cin;

@@ -38,8 +38,21 @@ class conv_2d(nn.Module):
         self.conv = nn.Sequential(nn.Conv2d(in_ch, out_ch, kernel_size=kernel, bias=bias), nn.BatchNorm2d(out_ch), act)
 
     def forward(self, x):
+        """x [B,Cin,N,1] -> [B,Cout,N,1] like the reference; 1x1 blocks on CUDA run as one fused
+        per-point GEMM + BatchNorm + activation (``forward_pm``), anything else through cuDNN."""
+        conv = self.conv[0]
+        if (x.is_cuda and x.dim() == 4 and x.shape[3] == 1 and conv.kernel_size == (1, 1)
+                and isinstance(self.conv[2], (nn.ReLU, nn.LeakyReLU)) and conv.out_channels % 4 == 0):
+            y = self.forward_pm(x.squeeze(3).transpose(1, 2))
+            return y.transpose(1, 2).unsqueeze(3)
         with exact_conv():
             return self.conv(x)
+
+    def forward_pm(self, x_pm):
+        """Point-major version: x_pm [..., Cin] -> [..., Cout]."""
+        conv, bn = self.conv[0], self._bn_tick()
+        return ops.linear_bn_act(x_pm, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                 self.training, self._slope(), bn.eps, bn.momentum)
 
     # ---- fused fast paths (point-major tensors) -------------------------------------------------
     def _bn_tick(self):
@@ -134,22 +147,43 @@ class adapt_layer_off(nn.Module):
         self.residual = conv_2d(trans_dim_in, fc_dim, 1)
 
     def forward(self, input_fea, input_loc):
-        fea = input_fea.squeeze(3) if input_fea.dim() == 4 else input_fea  # [B,C,N]
-        fidx = point_utils.farthest_point_sample(input_loc, self.num_node)
-        f_loc = point_utils.index_points(input_loc, fidx)
-        f_fea = point_utils.index_points(fea, fidx)
-        gidx = point_utils.query_ball_point(0.3, 64, input_loc, f_loc)
-        g_fea = point_utils.index_points(fea, gidx) - f_fea.unsqueeze(3)
-        with exact_conv():
-            seman_trans = self.pred_offset(g_fea)
-        g_loc = point_utils.index_points(input_loc, gidx) - f_loc.unsqueeze(3)
-        node_offset = (seman_trans * g_loc).mean(dim=-1)
+        """Reference signature: input_fea [B,C,N,1] (or [B,C,N]), input_loc [B,3,N] ->
+        (output_fea [B,2C,N,1], node_fea [B,C,num_node,1], node_offset [B,3,num_node])."""
+        fea = input_fea.squeeze(3) if input_fea.dim() == 4 else input_fea
+        out_pm, node_pm, off_pm = self.forward_pm(fea.transpose(1, 2), input_loc)
+        return out_pm.transpose(1, 2).unsqueeze(3), node_pm.transpose(1, 2).unsqueeze(3), off_pm.transpose(1, 2)
+
+    def forward_pm(self, fea, input_loc):
+        """Point-major core.  fea [B,N,C], input_loc [B,3,N] ->
+        (cat(fea, interpolated) [B,N,2C], node_fea [B,S,C], node_offset [B,S,3])."""
+        B, N, C = fea.shape
+        S = self.num_node
+        loc = input_loc.transpose(1, 2)  # [B,N,3] view
+        bi = torch.arange(B, device=fea.device).view(B, 1)
+        fidx = point_utils.farthest_point_sample(input_loc, S)                      # [B,S]
+        f_loc = loc[bi, fidx]                                                         # [B,S,3]
+        f_fea = fea[bi, fidx]                                                         # [B,S,C]
+        gidx = point_utils.query_ball_point(0.3, 64, input_loc, f_loc.transpose(1, 2))  # [B,S,64]
+        bi3 = bi.view(B, 1, 1)
+        g_fea = fea[bi3, gidx] - f_fea.unsqueeze(2)                                   # [B,S,64,C]
+        seman_trans = torch.tanh(ops.linear(g_fea, self.pred_offset[0].weight))       # [B,S,64,3]
+        g_loc = loc[bi3, gidx] - f_loc.unsqueeze(2)                                   # [B,S,64,3]
+        node_offset = (seman_trans * g_loc).mean(dim=2)                               # [B,S,3]
         node_loc = f_loc + node_offset
-        gidx2 = point_utils.query_ball_point(None, 64, input_loc, node_loc)
-        residual_fea = self.residual(fea.unsqueeze(3)).squeeze(3)
-        node_fea, _ = torch.max(point_utils.index_points(residual_fea, gidx2), dim=-1, keepdim=True)
-        output_fea = point_utils.upsample_inter(input_loc, node_loc, fea, node_fea, k=3).unsqueeze(3)
-        return output_fea, node_fea, node_offset
+        node_loc_cm = node_loc.transpose(1, 2)                                        # [B,3,S]
+        gidx2 = point_utils.query_ball_point(None, 64, input_loc, node_loc_cm)        # [B,S,64]
+        residual_fea = self.residual.forward_pm(fea)                                  # [B,N,C]
+        node_fea = residual_fea[bi3, gidx2].max(dim=2)[0]                             # [B,S,C]
+        # 3-NN inverse-squared-distance interpolation back to the points (point_utils.py:134-165)
+        idx3 = ops.three_nn(input_loc, node_loc_cm, 3).long()                         # [B,N,3]
+        nb = node_loc[bi3, idx3]                                                      # [B,N,3,3]
+        dots = (loc.unsqueeze(2) * nb).sum(-1)
+        dists = -2 * dots + (loc ** 2).sum(-1, keepdim=True) + (nb ** 2).sum(-1)
+        dists = torch.where(dists < 1e-10, torch.full_like(dists, 1e-10), dists)
+        weight = 1.0 / dists
+        weight = weight / weight.sum(dim=-1, keepdim=True)
+        interp = (node_fea[bi3, idx3] * weight.unsqueeze(-1)).sum(dim=2)              # [B,N,C]
+        return torch.cat((fea, interp), dim=2), node_fea, node_offset
 
 
 class focal_loss(nn.Module):

@@ -238,6 +238,118 @@ def mlp_bn_act_pool(x, weight, bias, gamma, beta, running_mean, running_var, tra
 
 
 # ------------------------------------------------------------------------------------------------
+# per-point linear layers
+# ------------------------------------------------------------------------------------------------
+class _LinearBnActFn(torch.autograd.Function):
+    """x [.., Cin] -> act(BN(x W^T + b)) [.., Cout], BatchNorm statistics over all leading rows."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, eps, momentum, slope):
+        lead = x.shape[:-1]
+        Cin = x.shape[-1]
+        x2 = x.reshape(-1, Cin)
+        if x2.stride(1) != 1 or x2.dtype != torch.float32:
+            x2 = x2.float().contiguous()
+        P = x2.shape[0]
+        Cout = weight.shape[0]
+        dev = x.device
+        w2 = weight.detach().reshape(Cout, Cin).contiguous()
+        y = torch.empty(P, Cout, dtype=torch.float32, device=dev)
+        out = torch.empty(P, Cout, dtype=torch.float32, device=dev)
+        save = torch.empty(2 * Cout, dtype=torch.float32, device=dev) if training else None
+        lib = _lib.load()
+        ws = _workspace(32 * Cout + 4096, dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sug_linear_bn_act_fwd(_ptr(x2), x2.stride(0), _ptr(w2), _ptr(None if bias is None else bias.detach()),
+                                                 _ptr(gamma.detach()), _ptr(beta.detach()), _ptr(running_mean),
+                                                 _ptr(running_var), P, Cin, Cout, eps, momentum, slope, int(training),
+                                                 _ptr(y), _ptr(out), Cout, _ptr(save), _ptr(ws), ws.numel(), _stream()),
+                       "sug_linear_bn_act_fwd")
+        if training:
+            ctx.save_for_backward(x2, w2, gamma, beta, y, save)
+            ctx.meta = (slope, weight.shape, bias is not None, tuple(x.shape))
+        return out.view(*lead, Cout)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x2, w2, gamma, beta, y, save = ctx.saved_tensors
+        slope, wshape, has_bias, xshape = ctx.meta
+        P, Cin = x2.shape
+        Cout = w2.shape[0]
+        dev = x2.device
+        g2 = gout.reshape(P, Cout)
+        if g2.stride(1) != 1 or g2.stride(0) % 4 != 0 or g2.data_ptr() % 16 != 0 or g2.dtype != torch.float32:
+            g2 = g2.float().contiguous()
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty(P, Cin, dtype=torch.float32, device=dev) if need_dx else None
+        dw = torch.empty(Cout, Cin, dtype=torch.float32, device=dev)
+        dbias = torch.empty(Cout, dtype=torch.float32, device=dev) if has_bias else None
+        dgamma = torch.empty(Cout, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(Cout, dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        ws = _workspace(32 * Cout + 4096, dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sug_linear_bn_act_bwd(_ptr(g2), g2.stride(0), _ptr(x2), x2.stride(0), _ptr(w2),
+                                                 _ptr(gamma.detach()), _ptr(beta.detach()), _ptr(y), _ptr(save), P, Cin,
+                                                 Cout, slope, _ptr(dx), Cin, _ptr(dw), _ptr(dbias), _ptr(dgamma),
+                                                 _ptr(dbeta), _ptr(ws), ws.numel(), _stream()), "sug_linear_bn_act_bwd")
+        return (None if dx is None else dx.view(xshape)), dw.view(wshape), dbias, dgamma, dbeta, None, None, None, None, None, None
+
+
+def linear_bn_act(x, weight, bias, gamma, beta, running_mean, running_var, training: bool, slope: float,
+                  eps: float = 1e-5, momentum: float = 0.1):
+    """1x1 conv over points + BatchNorm + ReLU/LeakyReLU on point-major rows (model_utils.py:8-32)."""
+    _need_cuda(x, weight)
+    return _LinearBnActFn.apply(x, weight, bias, gamma, beta, running_mean, running_var, bool(training), float(eps),
+                                float(momentum), float(slope))
+
+
+def _gemm_auto(a, b, bias=None, out=None):
+    """a [M,K] x b[N,K]^T (+bias) through the library's dispatcher (tensor cores when possible)."""
+    M, K = a.shape
+    N = b.shape[0]
+    c = torch.empty(M, N, dtype=torch.float32, device=a.device) if out is None else out
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        _lib.check(lib.sug_gemm_auto_f32(_ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), _ptr(bias),
+                                         _ptr(c), c.stride(0), M, N, K, _stream()), "sug_gemm_auto_f32")
+    return c
+
+
+class _LinearFn(torch.autograd.Function):
+    """x [.., K] -> x W^T + b  (fp32-accurate tensor-core GEMM)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K)
+        if x2.stride(1) != 1 or x2.dtype != torch.float32:
+            x2 = x2.float().contiguous()
+        w2 = weight.detach().reshape(weight.shape[0], K).contiguous()
+        y = _gemm_auto(x2, w2, None if bias is None else bias.detach())
+        ctx.save_for_backward(x2, w2)
+        ctx.meta = (tuple(x.shape), weight.shape, bias is not None)
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, w2 = ctx.saved_tensors
+        xshape, wshape, has_bias = ctx.meta
+        g2 = g.reshape(-1, w2.shape[0])
+        if g2.stride(1) != 1 or g2.dtype != torch.float32:
+            g2 = g2.float().contiguous()
+        dx = _gemm_auto(g2, w2.t()).view(xshape) if ctx.needs_input_grad[0] else None
+        dw = _gemm_auto(g2.t(), x2.t()).view(wshape) if ctx.needs_input_grad[1] else None
+        db = g2.sum(0) if has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    _need_cuda(x, weight)
+    return _LinearFn.apply(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------
 # MMD + Chamfer
 # ------------------------------------------------------------------------------------------------
 class _MmdFn(torch.autograd.Function):
