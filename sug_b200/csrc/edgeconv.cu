@@ -303,183 +303,11 @@ edge_bwd_main_kernel(const float* __restrict__ ab, const float* __restrict__ gha
   }
 }
 
-// ---- shared-memory staged gather (the production forward for N*CH*4 B <= 224 KB) --------------------
-// One CTA per (cloud, chunk of CH channels): the cloud's `a` rows for the chunk are staged once in
-// shared memory (pre-multiplied by sign(gamma) so "extreme" is always a max), then every warp walks
-// points: lane = channel, one conflict-free 128 B LDS per neighbour.  Per edge and channel:
-// FADD, compare/select (value + slot), FADD, FFMA.  BatchNorm sums are reduced per lane in fp64.
-template <int CH, bool TRAIN>
-__global__ void __launch_bounds__(512, 1)
-edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ idx, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, const float* __restrict__ mean_invstd, int N, int k,
-                        int Cout, float slope, float* __restrict__ ext, uint8_t* __restrict__ arg,
-                        float* __restrict__ ssum, double* __restrict__ sums, float* __restrict__ out, long long ldo) {
-  extern __shared__ __align__(16) float As[];  // [N][CH]
-  __shared__ double red[16][64];
-  constexpr int PPW = 32 / CH;  // points per warp instruction
-  const int c0 = blockIdx.x * CH;
-  const int b = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ch = lane % CH, sub = lane / CH;
-  const int ld = 2 * Cout;
-  const long long cb = (long long)b * N;
-  // stage A chunk, signed
-  {
-    constexpr int Q = CH / 4;
-    for (int e = tid; e < N * Q; e += 512) {
-      int n = e / Q, q = e - n * Q;
-      float4 v = __ldg(reinterpret_cast<const float4*>(ab + (cb + n) * ld + c0) + q);
-      float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0) + q);
-      v.x = g.x < 0.f ? -v.x : v.x;
-      v.y = g.y < 0.f ? -v.y : v.y;
-      v.z = g.z < 0.f ? -v.z : v.z;
-      v.w = g.w < 0.f ? -v.w : v.w;
-      reinterpret_cast<float4*>(As + (size_t)n * CH)[q] = v;
-    }
-  }
-  const float gch = __ldg(gamma + c0 + ch);
-  const float sgn = gch < 0.f ? -1.f : 1.f;
-  float sc = 0.f, sh = 0.f;
-  if (!TRAIN) {
-    float m = __ldg(mean_invstd + c0 + ch), is = __ldg(mean_invstd + Cout + c0 + ch);
-    sc = gch * is;
-    sh = __ldg(beta + c0 + ch) - m * sc;
-  }
-  __syncthreads();
-  double ds = 0.0, dq = 0.0;
-  for (int p0 = warp * PPW; p0 < N; p0 += 16 * PPW) {
-    const int i = p0 + sub;
-    if (i < N) {
-      const float bb = sgn * __ldg(ab + (cb + i) * ld + Cout + c0 + ch);
-      const int* ip = idx + (cb + i) * k;
-      float best = -INFINITY, s1 = 0.f, s2 = 0.f;
-      int bslot = 0;
-      for (int s0 = 0; s0 < k; s0 += 4) {
-        int j[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) j[u] = __ldg(ip + min(s0 + u, k - 1));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (s0 + u < k) {
-            const float y = As[(size_t)j[u] * CH + ch] + bb;
-            if (y > best) { best = y; bslot = s0 + u; }
-            if (TRAIN) {
-              s1 += y;
-              s2 = fmaf(y, y, s2);
-            }
-          }
-        }
-      }
-      const float e = best * sgn;
-      if (TRAIN) {
-        ext[(cb + i) * Cout + c0 + ch] = e;
-        ssum[(cb + i) * Cout + c0 + ch] = s1 * sgn;
-        arg[(cb + i) * Cout + c0 + ch] = (uint8_t)bslot;
-        ds += (double)(s1 * sgn);
-        dq += (double)s2;
-      } else {
-        out[(cb + i) * ldo + c0 + ch] = act_leaky(fmaf(sc, e, sh), slope);
-      }
-    }
-  }
-  if (TRAIN) {
-    red[warp][lane] = ds;
-    red[warp][32 + lane] = dq;
-    __syncthreads();
-    if (tid < CH) {
-      double a = 0.0, q = 0.0;
-      for (int w = 0; w < 16; ++w)
-        for (int u = 0; u < PPW; ++u) {
-          a += red[w][u * CH + tid];
-          q += red[w][32 + u * CH + tid];
-        }
-      atomicAdd(&sums[c0 + tid], a);
-      atomicAdd(&sums[Cout + c0 + tid], q);
-    }
-  }
-}
-
-// Backward twin: per (cloud, 16 channels) the cloud's ghat / b / arg rows are staged in shared
-// memory and every point sums over its in-edges (transposed graph) out of shared memory.
-__global__ void __launch_bounds__(512, 1)
-edge_bwd_smem_kernel(const float* __restrict__ ab, const float* __restrict__ ghat, const uint8_t* __restrict__ arg,
-                     const float* __restrict__ ssum, const int* __restrict__ rev_ptr, const int* __restrict__ rev_edge,
-                     const float* __restrict__ gamma, const float* __restrict__ mean_invstd,
-                     const double* __restrict__ gsums, int B, int N, int k, int Cout, float* __restrict__ dab,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  constexpr int CH = 16;
-  extern __shared__ __align__(16) float sm[];
-  float* Gh = sm;                                   // [N][16]
-  float* Bs = sm + (size_t)N * CH;                  // [N][16]
-  uint8_t* Ar = reinterpret_cast<uint8_t*>(sm + 2 * (size_t)N * CH);  // [N][16]
-  const int c0 = blockIdx.x * CH;
-  const int b = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ch = lane & 15, sub = lane >> 4;
-  const int ld = 2 * Cout;
-  const long long cb = (long long)b * N;
-  for (int e = tid; e < N * 4; e += 512) {
-    int n = e >> 2, q = e & 3;
-    reinterpret_cast<float4*>(Gh + (size_t)n * CH)[q] = __ldg(reinterpret_cast<const float4*>(ghat + (cb + n) * Cout + c0) + q);
-    reinterpret_cast<float4*>(Bs + (size_t)n * CH)[q] = __ldg(reinterpret_cast<const float4*>(ab + (cb + n) * ld + Cout + c0) + q);
-    reinterpret_cast<uchar4*>(Ar + (size_t)n * CH)[q] = __ldg(reinterpret_cast<const uchar4*>(arg + (cb + n) * Cout + c0) + q);
-  }
-  const int c = c0 + ch;
-  const double Md = (double)B * (double)N * (double)k;
-  const float mean = __ldg(mean_invstd + c), is = __ldg(mean_invstd + Cout + c);
-  const float sc = __ldg(gamma + c) * is;
-  const double G1 = gsums[c], G2 = gsums[Cout + c];
-  const float c1 = (float)(G1 / Md), c2 = (float)(G2 / Md) * is;
-  if (b == 0 && warp == 0 && sub == 0) {
-    dbeta[c] = (float)G1;
-    dgamma[c] = (float)G2;
-  }
-  __syncthreads();
-  const float kf = (float)k;
-  const int* rp = rev_ptr + (long long)b * (N + 1);
-  const int* re = rev_edge + cb * k;
-  for (int p0 = warp * 2; p0 < N; p0 += 32) {
-    const int jl = p0 + sub;
-    if (jl < N) {
-      const int lo = __ldg(rp + jl), hi = __ldg(rp + jl + 1);
-      float T = 0.f, Gs = 0.f;
-      for (int t = lo; t < hi; ++t) {
-        const int pk = __ldg(re + t);
-        const int i = pk >> 8;
-        const unsigned s = (unsigned)(pk & 255);
-        T += Bs[(size_t)i * CH + ch];
-        Gs += (Ar[(size_t)i * CH + ch] == s) ? Gh[(size_t)i * CH + ch] : 0.f;
-      }
-      const float deg = (float)(hi - lo);
-      const long long j = cb + jl;
-      const float aa = __ldg(ab + j * ld + c);
-      const float gg = Gh[(size_t)jl * CH + ch];
-      const float SS = __ldg(ssum + j * Cout + c);
-      dab[j * ld + Cout + c] = sc * (gg - kf * c1 - c2 * (SS - kf * mean));
-      dab[j * ld + c] = sc * (Gs - deg * c1 - c2 * (deg * (aa - mean) + T));
-    }
-  }
-}
-
 static int gather_grid(long long P, int Cout) {
   int ppb = 256 / (Cout >> 2);
   long long blocks = (P + ppb - 1) / ppb;
   long long cap = (long long)num_sms() * 8;
   return (int)(blocks < cap ? blocks : cap);
-}
-
-// Channel-chunk width of the shared-memory gather: 32 when that fills the GPU, 16 for narrow layers,
-// 0 (global-memory gather) when a cloud's chunk does not fit in shared memory.
-static int smem_chunk(int B, int N, int Cout) {
-  if (Cout % 32 == 0 && (size_t)N * 32 * 4 <= 220 * 1024 && (long long)B * (Cout / 32) >= num_sms()) return 32;
-  if (Cout % 16 == 0 && (size_t)N * 16 * 4 <= 220 * 1024) return 16;
-  if (Cout % 32 == 0 && (size_t)N * 32 * 4 <= 220 * 1024) return 32;
-  return 0;
-}
-
-static int smem_attr(const void* fn, size_t bytes) {
-  if (bytes > 48 * 1024) SUG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return 0;
 }
 
 }  // namespace sug
@@ -531,19 +359,8 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
     SUG_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cout, stream));
     {
       ProfScope ps(KC_EDGE_FWD, 4.0 * P * k * Cout, (double)P * (8.0 * Cout + 4.0 * k + 9.0 * Cout), stream);
-      const int CH = smem_chunk(B, N, Cout);
-      if (CH == 32) {
-        SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<32, true>, (size_t)N * 32 * 4));
-        edge_gather_smem_kernel<32, true><<<dim3(Cout / 32, B), 512, (size_t)N * 32 * 4, stream>>>(
-            ab, idx, gamma, beta, nullptr, N, k, Cout, slope, ext, arg, ssum, sums, nullptr, 0);
-      } else if (CH == 16) {
-        SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<16, true>, (size_t)N * 16 * 4));
-        edge_gather_smem_kernel<16, true><<<dim3(Cout / 16, B), 512, (size_t)N * 16 * 4, stream>>>(
-            ab, idx, gamma, beta, nullptr, N, k, Cout, slope, ext, arg, ssum, sums, nullptr, 0);
-      } else {
-        edge_gather_fwd_kernel<true><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, nullptr, (int)P, N, k, Cout, slope,
-                                                               ext, arg, ssum, sums, nullptr, 0);
-      }
+      edge_gather_fwd_kernel<true><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, nullptr, (int)P, N, k, Cout, slope,
+                                                             ext, arg, ssum, sums, nullptr, 0);
     }
     SUG_LAUNCH_CHECK();
     SUG_TRY(bn_finalize_stats(sums, Cout, (double)P * k, eps, momentum, running_mean, running_var,
@@ -560,19 +377,8 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
     SUG_TRY(bn_eval_stats(running_mean, running_var, Cout, eps, mi_eval, stream));
     {
       ProfScope ps(KC_EDGE_FWD, 2.0 * P * k * Cout, (double)P * (8.0 * Cout + 4.0 * k + 4.0 * Cout), stream);
-      const int CH = smem_chunk(B, N, Cout);
-      if (CH == 32) {
-        SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<32, false>, (size_t)N * 32 * 4));
-        edge_gather_smem_kernel<32, false><<<dim3(Cout / 32, B), 512, (size_t)N * 32 * 4, stream>>>(
-            ab, idx, gamma, beta, mi_eval, N, k, Cout, slope, nullptr, nullptr, nullptr, nullptr, out, ldo);
-      } else if (CH == 16) {
-        SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<16, false>, (size_t)N * 16 * 4));
-        edge_gather_smem_kernel<16, false><<<dim3(Cout / 16, B), 512, (size_t)N * 16 * 4, stream>>>(
-            ab, idx, gamma, beta, mi_eval, N, k, Cout, slope, nullptr, nullptr, nullptr, nullptr, out, ldo);
-      } else {
-        edge_gather_fwd_kernel<false><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, mi_eval, (int)P, N, k, Cout, slope,
-                                                                nullptr, nullptr, nullptr, nullptr, out, ldo);
-      }
+      edge_gather_fwd_kernel<false><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, mi_eval, (int)P, N, k, Cout, slope,
+                                                              nullptr, nullptr, nullptr, nullptr, out, ldo);
     }
     SUG_LAUNCH_CHECK();
   }
@@ -610,16 +416,8 @@ extern "C" int sug_edgeconv_bwd(const float* gout, int64_t ldg, const float* x, 
   SUG_LAUNCH_CHECK();
   {
     ProfScope ps(KC_EDGE_BWD_MAIN, 3.0 * P * k * Cout, (double)P * (8.0 * Cout + 9.0 * Cout + 4.0 * k + 8.0 * Cout), stream);
-    const size_t bsm = (size_t)N * 16 * 9;
-    if (Cout % 16 == 0 && bsm <= 220 * 1024) {
-      SUG_TRY(smem_attr((const void*)edge_bwd_smem_kernel, bsm));
-      edge_bwd_smem_kernel<<<dim3(Cout / 16, B), 512, bsm, stream>>>(ab, ghat, arg, ssum, rev_ptr, rev_edge, gamma,
-                                                                     save_mean_invstd, gsums, B, N, k, Cout, dab, dgamma,
-                                                                     dbeta);
-    } else {
-      edge_bwd_main_kernel<<<grid, 256, 0, stream>>>(ab, ghat, arg, ssum, rev_ptr, rev_edge, gamma, save_mean_invstd,
-                                                     gsums, P, N, k, Cout, dab, dgamma, dbeta);
-    }
+    edge_bwd_main_kernel<<<grid, 256, 0, stream>>>(ab, ghat, arg, ssum, rev_ptr, rev_edge, gamma, save_mean_invstd,
+                                                   gsums, P, N, k, Cout, dab, dgamma, dbeta);
   }
   SUG_LAUNCH_CHECK();
   // dWcat = dab^T x   ([2Cout, P] x [P, C])
