@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--mmd-scope", default="local", choices=["local", "global"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-all", action="store_true", help="time every kernel class (diagnostics)")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     return ap.parse_args()
 
 
@@ -170,7 +171,7 @@ def main():
 
     torch.manual_seed(666)  # train_dg_single_gpu.py:65
     model = Model.Net_MDA("DGCNN").to(dev).train()
-    opts = step.make_optimizers(model)
+    opts = step.make_optimizers(model, capturable=not args.no_graph)
     crit = model_utils.focal_loss(num_classes=10, gamma=0.0, alpha=[0.1] * 10)  # ClassWeighting / DLSA, uniform counts
     mmd_fn = sdist.global_mmd_cal if (args.mmd_scope == "global" and world > 1) else None
     hook = sdist.allreduce_grads if world > 1 else None
@@ -184,8 +185,7 @@ def main():
     dev_batches = [tuple(t.to(dev) for t in hb) for hb in pool]
     h2d_bytes = sum(t.numel() * t.element_size() for t in pool[0])
 
-    def run_step(batch):
-        d, l, dt, lt = batch
+    def run_step(d, l, dt, lt):
         if mmd_fn is None:
             return step.train_step(model, opts, d, l, dt, lt, crit, grad_hook=hook)
         out = step.sug_losses(model, d, l, dt, lt, crit, mmd_fn=mmd_fn)
@@ -205,26 +205,50 @@ def main():
 
     # ---- warm-up (untimed) + one instrumented step to find the dominant kernel class --------------
     for i in range(args.warmup):
-        run_step(dev_batches[i % len(dev_batches)])
+        run_step(*dev_batches[i % len(dev_batches)])
     _lib.prof_reset(mask=0xFFFFFFFF)
-    run_step(dev_batches[0])
+    run_step(*dev_batches[0])
     prof1 = _lib.prof_collect()
     dom = max(prof1.items(), key=lambda kv: kv[1]["ms"])[0]
     breakdown = {k: round(v["ms"], 4) for k, v in prof1.items() if v["launches"]}
 
+    # ---- the step as one CUDA graph (public API: step.GraphedTrainStep); eager fallback ---------------
+    prof_mask = 0xFFFFFFFF if args.profile_all else (1 << prof1[dom]["index"])
+    _lib.prof_reset(mask=prof_mask)
+    graphed, mode = None, "eager"
+    if not args.no_graph:
+        try:
+            for o in opts:
+                o.zero_grad(set_to_none=True)
+            graphed = step.GraphedTrainStep(model, opts, crit, B, N_POINTS, dev, mmd_fn=mmd_fn, grad_hook=hook)
+            graphed.warm(*dev_batches[0])
+            _lib.prof_reset(mask=prof_mask)  # count / time exactly the launches recorded into the graph
+            graphed.capture()
+            mode = "cuda_graph"
+        except Exception as e:  # keep measuring: the eager path is the same kernels
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            graphed = None
+            _lib.prof_reset(mask=prof_mask)
+    launches_per_capture = int(sum(v["launches"] for v in _lib.prof_collect().values())) if graphed else 0
+    if graphed is not None:
+        run_step = graphed
+        for i in range(3):
+            run_step(*dev_batches[i % len(dev_batches)])
+
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------------
-    _lib.prof_reset(mask=0xFFFFFFFF if args.profile_all else (1 << prof1[dom]["index"]))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         e0.record()
         for i in range(args.steps):
-            run_step(dev_batches[i % len(dev_batches)])
+            run_step(*dev_batches[i % len(dev_batches)])
         e1.record()
         barrier()
+        if not clk.lines:
+            time.sleep(0.25)  # very short timed regions: make sure nvidia-smi emitted at least one sample
     ms = e0.elapsed_time(e1)
     prof = _lib.prof_collect()
-    launches = int(sum(v["launches"] for v in prof.values()))
+    launches = launches_per_capture * args.steps if graphed else int(sum(v["launches"] for v in prof.values()))
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
@@ -233,15 +257,16 @@ def main():
     value = clouds_per_step * args.steps / (ms / 1e3)
 
     # ---- timed region 2: end to end from pinned host memory, loss read back every step --------------
-    _lib.prof_reset(mask=0)
+    if graphed is None:
+        _lib.prof_reset(mask=0)
     host_loss = torch.empty((), dtype=torch.float32).pin_memory()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(args.steps):
         hb = pool[i % len(pool)]
-        batch = tuple(t.to(dev, non_blocking=True) for t in hb)
-        out = run_step(batch)
+        batch = hb if graphed is not None else tuple(t.to(dev, non_blocking=True) for t in hb)
+        out = run_step(*batch)
         host_loss.copy_(out["loss"].detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         float(host_loss)
@@ -261,6 +286,9 @@ def main():
     # ---- roofline of the dominant kernel class --------------------------------------------------------
     pk = peaks()
     d = prof[dom]
+    if graphed is not None:
+        # graph replays re-record the same event pairs: the totals are those of the LAST timed step
+        d = dict(d, launches=d["timed"], flops=d["flops"], bytes=d["bytes"])
     per_launch_s = (d["ms"] / 1e3) / max(1, d["timed"])
     tensor_bound = dom in ("gemm_simt", "gemm_tc", "knn_simt", "knn_tc")
     if tensor_bound:
@@ -272,7 +300,7 @@ def main():
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                 "traffic": None}
     roof.update({"kernel": dom, "launches_timed": int(d["timed"]), "avg_launch_us": per_launch_s * 1e6,
-                 "share_of_step": d["ms"] / ms, "peak_source": pk["src"] + (" bf16 sustained" if tensor_bound else " copy")})
+                 "share_of_step": d["ms"] / (ms / args.steps if graphed is not None else ms), "peak_source": pk["src"] + (" bf16 sustained" if tensor_bound else " copy")})
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -281,7 +309,7 @@ def main():
                                    "CE(2 heads x 2 sub-domains) + GEO/SEM soft-MMD with SDA weights "
                                    "(DG_unified_loss_onedataset_shapenet.yaml)",
                        "clouds_per_step_per_gpu": 2 * B, "batch_per_subdomain": B, "points": N_POINTS, "k": 20,
-                       "classes": 10, "parallelism": f"dp{world}", "mmd_scope": args.mmd_scope,
+                       "classes": 10, "parallelism": f"dp{world}", "mmd_scope": args.mmd_scope, "execution": mode,
                        "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

@@ -70,7 +70,7 @@ struct ProfState {
 };
 static ProfState g_prof;
 
-ProfScope::ProfScope(int c, double fl, double by, cudaStream_t s) : cls(c), stream(s), slot(-1) {
+ProfScope::ProfScope(int c, double fl, double by, cudaStream_t s) : cls(c), stream(s), slot(-1), capturing(false) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
   g_prof.launches[c] += 1;
   g_prof.flops[c] += fl;
@@ -78,7 +78,8 @@ ProfScope::ProfScope(int c, double fl, double by, cudaStream_t s) : cls(c), stre
   if (g_prof.mask & (1u << c)) {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(s, &st);
-    if (st == cudaStreamCaptureStatusNone && g_prof.used < 400000) {
+    capturing = st != cudaStreamCaptureStatusNone;
+    if (g_prof.used < 400000) {
       if (g_prof.ev.size() < 2 * (g_prof.used + 1)) {
         cudaEvent_t a, b;
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
@@ -88,12 +89,17 @@ ProfScope::ProfScope(int c, double fl, double by, cudaStream_t s) : cls(c), stre
       }
       slot = (int)g_prof.used++;
       g_prof.ev_cls[slot] = c;
-      cudaEventRecord(g_prof.ev[2 * slot], s);
+      // inside a stream capture the events become external event-record nodes of the graph, so every
+      // replay re-times the launch (bench.py reads the last replay)
+      if (capturing) cudaEventRecordWithFlags(g_prof.ev[2 * slot], s, cudaEventRecordExternal);
+      else cudaEventRecord(g_prof.ev[2 * slot], s);
     }
   }
 }
 ProfScope::~ProfScope() {
-  if (slot >= 0) cudaEventRecord(g_prof.ev[2 * slot + 1], stream);
+  if (slot < 0) return;
+  if (capturing) cudaEventRecordWithFlags(g_prof.ev[2 * slot + 1], stream, cudaEventRecordExternal);
+  else cudaEventRecord(g_prof.ev[2 * slot + 1], stream);
 }
 
 int bn_finalize_stats(const double* sums, int C, double count, float eps, float momentum, float* running_mean,

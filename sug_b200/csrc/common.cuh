@@ -62,6 +62,7 @@ struct ProfScope {
   int cls;
   cudaStream_t stream;
   int slot;
+  bool capturing;
   ProfScope(int cls, double flops, double bytes, cudaStream_t stream);
   ~ProfScope();
 };

@@ -8,12 +8,25 @@ import torch
 from . import ops
 
 
+_FPS_START_FEED = None  # set by step.GraphedTrainStep: start indices come from a static device buffer
+
+
+def set_fps_start_feed(feed):
+    """``feed()`` must return a device int32 tensor [B] of FPS start indices (drawn by the caller
+    with ``torch.randint`` exactly like the reference).  None restores the in-place draw."""
+    global _FPS_START_FEED
+    _FPS_START_FEED = feed
+
+
 def farthest_point_sample(xyz, npoint):
     """point_utils.py:5-26.  xyz [B,3,N] -> int64 [B,npoint].  The start index is drawn with
     ``torch.randint`` on the CPU generator exactly like line 17, so seeded runs consume the RNG
     identically to the reference."""
     B, _, N = xyz.shape
-    start = torch.randint(0, N, (B,), dtype=torch.long)
+    if _FPS_START_FEED is not None:
+        start = _FPS_START_FEED()
+    else:
+        start = torch.randint(0, N, (B,), dtype=torch.long)
     return ops.fps(xyz, npoint, start).long()
 
 

@@ -45,16 +45,16 @@ def sug_losses(model, data, label, data_t, label_t, criterion, cfg=SUG_CFG, mmd_
             "loss_sem": loss_sem, "pred_s1": pred_s1, "pred_t1": pred_t1}
 
 
-def make_optimizers(model, opt=OPT_CFG):
-    """train_dg_single_gpu.py:191-203: three Adam optimizers; ``g`` is stepped by two of them."""
+def make_optimizers(model, opt=OPT_CFG, capturable=False):
+    """train_dg_single_gpu.py:191-203: three Adam optimizers; ``g`` is stepped by two of them.
+    ``capturable=True`` keeps Adam's step counters on the device (needed inside a CUDA graph)."""
     lr, wd = opt["LR"], opt["WEIGHT_DECAY"]
+    kw = dict(weight_decay=wd, capturable=capturable)
     params = [{'params': v} for k, v in model.g.named_parameters() if 'pred_offset' not in k]
-    opt_g = torch.optim.Adam(params, lr=lr, weight_decay=wd)
-    opt_c = torch.optim.Adam([{'params': model.c1.parameters()}, {'params': model.c2.parameters()}], lr=lr,
-                             weight_decay=wd)
+    opt_g = torch.optim.Adam(params, lr=lr, **kw)
+    opt_c = torch.optim.Adam([{'params': model.c1.parameters()}, {'params': model.c2.parameters()}], lr=lr, **kw)
     opt_dis = torch.optim.Adam([{'params': model.g.parameters()}, {'params': model.attention_s.parameters()},
-                                {'params': model.attention_t.parameters()}], lr=lr * opt["LR_SCALER"],
-                               weight_decay=wd)
+                                {'params': model.attention_t.parameters()}], lr=lr * opt["LR_SCALER"], **kw)
     return opt_dis, opt_g, opt_c
 
 
@@ -71,3 +71,107 @@ def train_step(model, optimizers, data, label, data_t, label_t, criterion, cfg=S
     for o in (optimizers[1], optimizers[2], optimizers[0]):
         o.zero_grad()
     return out
+
+
+class GraphedTrainStep:
+    """The whole training step (4 forwards, losses, backward, 3 Adam updates) as ONE CUDA graph.
+
+    Eager execution of the step is bound by the ~2 000 Python-side launches, not by the GPU; the
+    graph removes that.  Shapes are static (``batch`` clouds of ``points`` points per sub-domain).
+    Host-side state the reference keeps per call is preserved:
+      * FPS start indices are still drawn with ``torch.randint`` on the CPU generator, four draws per
+        step in call order (point_utils.py:17), and copied into a static device buffer;
+      * ``focal_loss`` re-gathers its own ``alpha`` on every call (model_utils.py:168); inside the graph
+        every step starts from the constructor's alpha, which is identical for the uniform class
+        weights used here.
+    ``optimizers`` must be built with ``make_optimizers(..., capturable=True)``.
+    """
+
+    def __init__(self, model, optimizers, criterion, batch, points, device, cfg=SUG_CFG, mmd_fn=None,
+                 grad_hook=None, warmup=3):
+        from . import point_utils
+        self.model, self.opts, self.crit = model, optimizers, criterion
+        self.cfg, self.mmd_fn, self.hook = cfg, (mmd_fn or mmd.mmd_cal), grad_hook
+        self.N = points
+        dev = torch.device(device)
+        self.data = torch.zeros(batch, 3, points, 1, device=dev)
+        self.data_t = torch.zeros(batch, 3, points, 1, device=dev)
+        self.label = torch.zeros(batch, dtype=torch.long, device=dev)
+        self.label_t = torch.zeros(batch, dtype=torch.long, device=dev)
+        self.fps_dev = torch.zeros(4, batch, dtype=torch.int32, device=dev)
+        self.fps_host = torch.zeros(4, batch, dtype=torch.int32).pin_memory()
+        self._call = 0
+        self._alpha0 = criterion.alpha.detach().clone().to(dev) if hasattr(criterion, "alpha") else None
+
+        def feed():
+            t = self.fps_dev[self._call % 4]
+            self._call += 1
+            return t
+        self._feed = feed
+        self._pu = point_utils
+        self.graph = None
+        self.out = None
+
+    def _body(self):
+        self._call = 0
+        if self._alpha0 is not None:
+            self.crit.alpha = self._alpha0
+        out = sug_losses(self.model, self.data, self.label, self.data_t, self.label_t, self.crit, self.cfg, self.mmd_fn)
+        out["loss"].backward()
+        if self.hook is not None:
+            self.hook(self.model)
+        for o in self.opts:
+            o.step()
+        return {k: v.detach() for k, v in out.items()}
+
+    def _draw_fps(self):
+        for i in range(4):  # same CPU-RNG consumption as four eager forwards
+            self.fps_host[i] = torch.randint(0, self.N, (self.fps_host.shape[1],), dtype=torch.long).to(torch.int32)
+        self.fps_dev.copy_(self.fps_host, non_blocking=True)
+
+    def warm(self, data, label, data_t, label_t, iters=3):
+        """Eager warm-up on a side stream (required before capture; these passes DO train the model)."""
+        for dst, src in ((self.data, data), (self.label, label), (self.data_t, data_t), (self.label_t, label_t)):
+            dst.copy_(src)
+        self._pu.set_fps_start_feed(self._feed)
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(iters):
+                    self._draw_fps()
+                    self._body()
+                    for o in self.opts:
+                        o.zero_grad(set_to_none=True)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+        finally:
+            self._pu.set_fps_start_feed(None)
+        return self
+
+    def capture(self):
+        """Record the step into a CUDA graph (call ``warm`` first).  Gradients must be None so that
+        the backward's first write of every ``.grad`` is an assignment inside the graph's pool."""
+        for o in self.opts:
+            o.zero_grad(set_to_none=True)
+        self._pu.set_fps_start_feed(self._feed)
+        try:
+            self._draw_fps()
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._body()
+        finally:
+            self._pu.set_fps_start_feed(None)
+        torch.cuda.synchronize()
+        return self
+
+    def __call__(self, data, label, data_t, label_t):
+        """One training step.  Inputs may live on the host (pinned) or on the device."""
+        self.data.copy_(data, non_blocking=True)
+        self.label.copy_(label, non_blocking=True)
+        self.data_t.copy_(data_t, non_blocking=True)
+        self.label_t.copy_(label_t, non_blocking=True)
+        self._draw_fps()
+        self.graph.replay()
+        return self.out
