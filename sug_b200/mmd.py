@@ -19,8 +19,9 @@ sigma_list = [0.01, 0.1, 1, 10, 100]  # mmd.py:23
 def create_one_hot_labels(original_labels, num_class=10):
     """utils/common_utils.py:161-164 (built on the labels' device)."""
     one_hot = torch.zeros(original_labels.shape[0], num_class, device=original_labels.device)
-    one_hot[torch.arange(original_labels.shape[0], device=original_labels.device), original_labels] = 1
-    return one_hot
+    # scatter_ with a Python scalar stays on the device (an indexed assignment of `1` would stage a CPU
+    # scalar tensor, which CUDA-graph capture forbids)
+    return one_hot.scatter_(1, original_labels.view(-1, 1).long(), 1.0)
 
 
 def mmd_cal(label_s, feat_s, label_t, feat_t, args: dict, data_s=None, data_t=None, KPC=False):

@@ -585,3 +585,51 @@ def test_full_size_properties(S):
     assert float((o1 - o2).abs().max()) <= 1e-5 * float(o1.abs().max())
     # BatchNorm: per-channel statistics of the pre-activation are (0, 1) => running_mean moved by 0.1*mean
     assert int(blk.conv[1].num_batches_tracked) == 2
+
+
+def test_graphed_step_matches_eager(S):
+    """The CUDA-graph step (step.GraphedTrainStep) must train exactly like the eager step: same RNG
+    consumption for FPS, same losses and weights after a few steps."""
+    B = 12
+    batches = []
+    for i in range(2):
+        d, l = O.synth_clouds(B, 1024, 10 + 2 * i)
+        dt, lt = O.synth_clouds(B, 1024, 11 + 2 * i)
+        batches.append(tuple(t.to(DEV) for t in (d, l, dt, lt)))
+
+    def build():
+        net = _load(S.Model.Net_MDA("DGCNN"), "Net_MDA:DGCNN").train()
+        for hd in (net.c1, net.c2):
+            hd.dropout1.p = hd.dropout2.p = 0.0
+        opts = S.step.make_optimizers(net, capturable=True)
+        crit = S.model_utils.focal_loss(num_classes=10, gamma=0.0, alpha=[0.1] * 10)
+        return net, opts, crit
+
+    # eager: 3 warm-up-equivalent steps + 3 compared steps
+    net_e, opts_e, crit_e = build()
+    torch.manual_seed(5)
+    losses_e = []
+    for i in range(7):
+        out = S.step.train_step(net_e, opts_e, *batches[i % 2], crit_e)
+        losses_e.append(float(out["loss"]))
+    # graphed: warm (3 eager passes) + capture pass (1) + 3 replays == 7 steps
+    net_g, opts_g, crit_g = build()
+    torch.manual_seed(5)
+    gs = S.step.GraphedTrainStep(net_g, opts_g, crit_g, B, 1024, DEV)
+    gs.warm(*batches[0], iters=0)
+    losses_g = []
+    for i in range(3):  # eager steps through the same object path
+        out = S.step.train_step(net_g, opts_g, *batches[i % 2], crit_g)
+        losses_g.append(float(out["loss"]))
+    gs.data.copy_(batches[1][0]); gs.label.copy_(batches[1][1]); gs.data_t.copy_(batches[1][2]); gs.label_t.copy_(batches[1][3])
+    gs.capture()  # the capture pass is step 4 (inputs of batch 1)
+    losses_g.append(float(gs.out["loss"]))
+    for i in range(4, 7):
+        losses_g.append(float(gs(*batches[i % 2])["loss"]))
+    print("eager  :", [f"{v:.6f}" for v in losses_e])
+    print("graphed:", [f"{v:.6f}" for v in losses_g])
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) <= 2e-4 * abs(a), (losses_e, losses_g)
+    pe, pg = dict(net_e.named_parameters()), dict(net_g.named_parameters())
+    for k in ("g.conv1.conv.0.weight", "g.conv5.weight", "c1.mlp3.weight", "attention_s.bn.weight"):
+        assert relerr(pg[k], pe[k]) < 1e-4, k
