@@ -303,11 +303,174 @@ edge_bwd_main_kernel(const float* __restrict__ ab, const float* __restrict__ gha
   }
 }
 
+// ---- shared-memory staged forward gather ------------------------------------------------------------
+// One CTA per (cloud, chunk of CH channels).  The cloud's `a` rows for the chunk are staged once in
+// shared memory, pre-multiplied by sign(gamma) so that "extreme" is always a max.  Because
+// y_ij = a_j + b_i with b_i constant over the k neighbours, the arg-max over y is the arg-max over a,
+// and the BatchNorm sums factor as
+//     sum y   = sum_i (S_i + k b_i),                         S_i = sum_{j in N(i)} a_j
+//     sum y^2 = sum_j deg_j a_j^2 + sum_i (2 b_i S_i + k b_i^2)      (deg_j = in-degree of j)
+// so the per-edge work is one conflict-free LDS.128 and, per channel, compare + 2 selects + 1 add.
+// Lanes own 4 channels; a warp serves 32*4/CH points per step; neighbour lists are staged per warp.
+__global__ void knn_degree_kernel(const int* __restrict__ idx, long long E, int N, int k, int* __restrict__ deg) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    const long long cloud = e / ((long long)N * k);
+    atomicAdd(deg + cloud * N + __ldg(idx + e), 1);
+  }
+}
+
+template <int CH, bool TRAIN>
+__global__ void __launch_bounds__(512, 1)
+edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ idx, const int* __restrict__ deg,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        const float* __restrict__ mean_invstd, int N, int k, int Cout, float slope,
+                        float* __restrict__ ext, uint8_t* __restrict__ arg, float* __restrict__ ssum,
+                        double* __restrict__ sums, float* __restrict__ out, long long ldo) {
+  constexpr int Q = CH / 4;      // float4 lanes per point
+  constexpr int PPW = 32 / Q;    // points per warp step
+  extern __shared__ __align__(16) float smem_f[];
+  float* As = smem_f;                                        // [N][CH]
+  int* widx = reinterpret_cast<int*>(smem_f + (size_t)N * CH);  // [16 warps][PPW * k]
+  __shared__ double red[512][8];                             // stats partials per thread
+  const int c0 = blockIdx.x * CH;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = lane % Q, sub = lane / Q;
+  const int ld = 2 * Cout;
+  const long long cb = (long long)b * N;
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + (tid % Q));
+  // ---- stage the signed A chunk; deg-weighted sum of squares on the way ----
+  double dsq[4] = {0, 0, 0, 0};
+  for (int e = tid; e < N * Q; e += 512) {  // 512 % Q == 0  =>  this thread's quad index is fixed
+    const int n = e / Q, qq = e - n * Q;
+    float4 v = __ldg(reinterpret_cast<const float4*>(ab + (cb + n) * ld + c0) + qq);
+    if (TRAIN) {
+      const float dg = (float)__ldg(deg + cb + n);
+      dsq[0] += (double)(dg * v.x * v.x);
+      dsq[1] += (double)(dg * v.y * v.y);
+      dsq[2] += (double)(dg * v.z * v.z);
+      dsq[3] += (double)(dg * v.w * v.w);
+    }
+    v.x = g4.x < 0.f ? -v.x : v.x;
+    v.y = g4.y < 0.f ? -v.y : v.y;
+    v.z = g4.z < 0.f ? -v.z : v.z;
+    v.w = g4.w < 0.f ? -v.w : v.w;
+    reinterpret_cast<float4*>(As + (size_t)n * CH)[qq] = v;
+  }
+  // per-lane constants for the channels this lane owns in the gather phase
+  const float4 gq = __ldg(reinterpret_cast<const float4*>(gamma + c0) + q);
+  const float sg[4] = {gq.x < 0.f ? -1.f : 1.f, gq.y < 0.f ? -1.f : 1.f, gq.z < 0.f ? -1.f : 1.f, gq.w < 0.f ? -1.f : 1.f};
+  float sc[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0};
+  if (!TRAIN) {
+    const float gg[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + 4 * q + u;
+      const float m = __ldg(mean_invstd + c), is = __ldg(mean_invstd + Cout + c);
+      sc[u] = gg[u] * is;
+      sh[u] = __ldg(beta + c) - m * sc[u];
+    }
+  }
+  __syncthreads();
+  double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+  int* wi = widx + warp * (PPW * k);
+  const float kf = (float)k;
+  for (int p0 = warp * PPW; p0 < N; p0 += 16 * PPW) {
+    // stage this step's neighbour lists (PPW consecutive points => PPW*k consecutive ints)
+    const int cnt = min(PPW, N - p0) * k;
+    __syncwarp();
+    for (int e = lane; e < cnt; e += 32) wi[e] = __ldg(idx + (cb + p0) * k + e);
+    __syncwarp();
+    const int i = p0 + sub;
+    if (i < N) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(ab + (cb + i) * ld + Cout + c0) + q);
+      float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      int bslot[4] = {0, 0, 0, 0};
+      float s1[4] = {0, 0, 0, 0};
+      const int* myi = wi + sub * k;
+#pragma unroll 4
+      for (int s = 0; s < k; ++s) {
+        const int j = myi[s];
+        const float4 a4 = reinterpret_cast<const float4*>(As + (size_t)j * CH)[q];
+        const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool gt = aa[u] > best[u];
+          best[u] = gt ? aa[u] : best[u];
+          bslot[u] = gt ? s : bslot[u];
+          if (TRAIN) s1[u] += aa[u];
+        }
+      }
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      float e4[4], S4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        e4[u] = best[u] * sg[u] + bb[u];
+        const float sa = s1[u] * sg[u];  // S^a_i (unsigned)
+        S4[u] = fmaf(kf, bb[u], sa);
+        if (TRAIN) {
+          ds[u] += (double)S4[u];
+          dq[u] += (double)(2.f * bb[u] * sa + kf * bb[u] * bb[u]);
+        }
+      }
+      if (TRAIN) {
+        reinterpret_cast<float4*>(ext + (cb + i) * Cout + c0)[q] = make_float4(e4[0], e4[1], e4[2], e4[3]);
+        reinterpret_cast<float4*>(ssum + (cb + i) * Cout + c0)[q] = make_float4(S4[0], S4[1], S4[2], S4[3]);
+        reinterpret_cast<uchar4*>(arg + (cb + i) * Cout + c0)[q] =
+            make_uchar4((unsigned char)bslot[0], (unsigned char)bslot[1], (unsigned char)bslot[2], (unsigned char)bslot[3]);
+      } else {
+        float4 o;
+        o.x = act_leaky(fmaf(sc[0], e4[0], sh[0]), slope);
+        o.y = act_leaky(fmaf(sc[1], e4[1], sh[1]), slope);
+        o.z = act_leaky(fmaf(sc[2], e4[2], sh[2]), slope);
+        o.w = act_leaky(fmaf(sc[3], e4[3], sh[3]), slope);
+        *reinterpret_cast<float4*>(out + (cb + i) * ldo + c0 + 4 * q) = o;
+      }
+    }
+  }
+  if (TRAIN) {
+    // thread t owns quad (t % Q) in both phases (512 % Q == 0 and 32 % Q == 0)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      red[tid][u] = ds[u];
+      red[tid][4 + u] = dq[u] + dsq[u];
+    }
+    __syncthreads();
+    if (tid < CH) {
+      const int qq = tid >> 2, u = tid & 3;
+      double a = 0.0, s2 = 0.0;
+      for (int t = qq; t < 512; t += Q) {
+        a += red[t][u];
+        s2 += red[t][4 + u];
+      }
+      atomicAdd(&sums[c0 + tid], a);
+      atomicAdd(&sums[Cout + c0 + tid], s2);
+    }
+  }
+}
+
 static int gather_grid(long long P, int Cout) {
   int ppb = 256 / (Cout >> 2);
   long long blocks = (P + ppb - 1) / ppb;
   long long cap = (long long)num_sms() * 8;
   return (int)(blocks < cap ? blocks : cap);
+}
+
+static size_t smem_bytes_gather(int N, int CH, int k) {
+  return (size_t)N * CH * 4 + (size_t)16 * (128 / CH) * k * 4;
+}
+// Channel-chunk width of the shared-memory gather: 32 when that still fills the GPU, 16 for narrow
+// layers, 0 (global-memory gather) when a cloud's chunk does not fit in shared memory.
+static int smem_chunk(int B, int N, int Cout, int k) {
+  const size_t cap = 200 * 1024;
+  if (Cout % 32 == 0 && smem_bytes_gather(N, 32, k) <= cap && (long long)B * (Cout / 32) >= num_sms()) return 32;
+  if (Cout % 16 == 0 && smem_bytes_gather(N, 16, k) <= cap) return 16;
+  if (Cout % 32 == 0 && smem_bytes_gather(N, 32, k) <= cap) return 32;
+  return 0;
+}
+static int smem_attr(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024) SUG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
 }
 
 }  // namespace sug
@@ -320,7 +483,7 @@ extern "C" size_t sug_edgeconv_ws_bytes(int B, int N, int C, int Cout, int k) {
   size_t w = align_up(sizeof(float) * 2 * (size_t)Cout * C, 256);
   size_t s = align_up(sizeof(double) * 2 * (size_t)Cout, 256);
   size_t gh = align_up(sizeof(float) * P * Cout, 256);
-  return 2 * w + s + gh + 1024;
+  return 2 * w + 2 * s + gh + align_up(sizeof(int) * P, 256) + 2048;
 }
 
 static int edge_check(int B, int N, int C, int Cout, int k) {
@@ -346,6 +509,7 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
   float* wcat = W.take<float>(2 * (size_t)Cout * C);
   double* sums = W.take<double>(2 * (size_t)Cout);
   float* mi_eval = W.take<float>(2 * (size_t)Cout);
+  int* deg = W.take<int>((size_t)P);
   if (!W.ok()) { set_error("edgeconv_fwd: workspace too small (%zu B)", ws_bytes); return SUG_E_WORKSPACE; }
 
   {
@@ -359,8 +523,24 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
     SUG_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cout, stream));
     {
       ProfScope ps(KC_EDGE_FWD, 4.0 * P * k * Cout, (double)P * (8.0 * Cout + 4.0 * k + 9.0 * Cout), stream);
-      edge_gather_fwd_kernel<true><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, nullptr, (int)P, N, k, Cout, slope,
-                                                             ext, arg, ssum, sums, nullptr, 0);
+      const int CH = smem_chunk(B, N, Cout, k);
+      if (CH != 0) {
+        SUG_CUDA(cudaMemsetAsync(deg, 0, sizeof(int) * P, stream));
+        knn_degree_kernel<<<num_sms() * 4, 256, 0, stream>>>(idx, (long long)P * k, N, k, deg);
+        const size_t sm = smem_bytes_gather(N, CH, k);
+        if (CH == 32) {
+          SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<32, true>, sm));
+          edge_gather_smem_kernel<32, true><<<dim3(Cout / 32, B), 512, sm, stream>>>(
+              ab, idx, deg, gamma, beta, nullptr, N, k, Cout, slope, ext, arg, ssum, sums, nullptr, 0);
+        } else {
+          SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<16, true>, sm));
+          edge_gather_smem_kernel<16, true><<<dim3(Cout / 16, B), 512, sm, stream>>>(
+              ab, idx, deg, gamma, beta, nullptr, N, k, Cout, slope, ext, arg, ssum, sums, nullptr, 0);
+        }
+      } else {
+        edge_gather_fwd_kernel<true><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, nullptr, (int)P, N, k, Cout, slope,
+                                                               ext, arg, ssum, sums, nullptr, 0);
+      }
     }
     SUG_LAUNCH_CHECK();
     SUG_TRY(bn_finalize_stats(sums, Cout, (double)P * k, eps, momentum, running_mean, running_var,
@@ -377,8 +557,20 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
     SUG_TRY(bn_eval_stats(running_mean, running_var, Cout, eps, mi_eval, stream));
     {
       ProfScope ps(KC_EDGE_FWD, 2.0 * P * k * Cout, (double)P * (8.0 * Cout + 4.0 * k + 4.0 * Cout), stream);
-      edge_gather_fwd_kernel<false><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, mi_eval, (int)P, N, k, Cout, slope,
-                                                              nullptr, nullptr, nullptr, nullptr, out, ldo);
+      const int CH = smem_chunk(B, N, Cout, k);
+      const size_t sm = CH ? smem_bytes_gather(N, CH, k) : 0;
+      if (CH == 32) {
+        SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<32, false>, sm));
+        edge_gather_smem_kernel<32, false><<<dim3(Cout / 32, B), 512, sm, stream>>>(
+            ab, idx, nullptr, gamma, beta, mi_eval, N, k, Cout, slope, nullptr, nullptr, nullptr, nullptr, out, ldo);
+      } else if (CH == 16) {
+        SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<16, false>, sm));
+        edge_gather_smem_kernel<16, false><<<dim3(Cout / 16, B), 512, sm, stream>>>(
+            ab, idx, nullptr, gamma, beta, mi_eval, N, k, Cout, slope, nullptr, nullptr, nullptr, nullptr, out, ldo);
+      } else {
+        edge_gather_fwd_kernel<false><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, mi_eval, (int)P, N, k, Cout, slope,
+                                                                nullptr, nullptr, nullptr, nullptr, out, ldo);
+      }
     }
     SUG_LAUNCH_CHECK();
   }

@@ -138,6 +138,135 @@ int gemm_simt_f32(const float* a, int64_t sam, int64_t sak, const float* b, int6
   return 0;
 }
 
+
+// ---- skinny shapes (HBM-bound, no tile reuse to exploit) -------------------------------------------
+// K <= 8 (the xyz layers: K = 3 / 6): every thread owns one row m, keeps A(m, 0..K) in registers and
+// streams the N outputs with float4 stores; B (N x K) sits in shared memory.
+__global__ void __launch_bounds__(256)
+skinny_k_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ Bm, long long sbn,
+                long long sbk, const float* __restrict__ bias, float* __restrict__ C, long long ldc, int M, int N, int K) {
+  extern __shared__ float sB[];  // [K][N] + bias[N]
+  for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
+    int n = e % N, k = e / N;
+    sB[k * N + n] = __ldg(Bm + (long long)n * sbn + (long long)k * sbk);
+  }
+  for (int n = threadIdx.x; n < N; n += blockDim.x) sB[K * N + n] = bias ? __ldg(bias + n) : 0.f;
+  __syncthreads();
+  const bool vec = (N % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  // a warp covers 32 consecutive n-quads of one row at a time => fully coalesced 512 B stores
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (long long m = (long long)blockIdx.x * 8 + wib; m < M; m += (long long)gridDim.x * 8) {
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = k < K ? __ldg(A + m * sam + (long long)k * sak) : 0.f;
+    if (vec) {
+      for (int n4 = lane; n4 < N / 4; n4 += 32) {
+        float4 o = *reinterpret_cast<const float4*>(sB + K * N + 4 * n4);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k < K) {
+            const float4 b = *reinterpret_cast<const float4*>(sB + k * N + 4 * n4);
+            o.x = fmaf(a[k], b.x, o.x); o.y = fmaf(a[k], b.y, o.y); o.z = fmaf(a[k], b.z, o.z); o.w = fmaf(a[k], b.w, o.w);
+          }
+        }
+        *reinterpret_cast<float4*>(C + m * ldc + 4 * n4) = o;
+      }
+    } else {
+      for (int n = lane; n < N; n += 32) {
+        float o = sB[K * N + n];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < K) o = fmaf(a[k], sB[k * N + n], o);
+        C[m * ldc + n] = o;
+      }
+    }
+  }
+}
+
+// N <= 8, A k-contiguous, moderate K (e.g. the 64 -> 3 offset head): one thread per row m, B in smem.
+__global__ void __launch_bounds__(256)
+skinny_n_kernel(const float* __restrict__ A, long long sam, const float* __restrict__ Bm, long long sbn, long long sbk,
+                const float* __restrict__ bias, float* __restrict__ C, long long ldc, int M, int N, int K) {
+  extern __shared__ float sB[];  // [N][K]
+  for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
+    int k = e % K, n = e / K;
+    sB[n * K + k] = __ldg(Bm + (long long)n * sbn + (long long)k * sbk);
+  }
+  __syncthreads();
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n] = (bias && n < N) ? __ldg(bias + n) : 0.f;
+    const float* ar = A + m * sam;
+    for (int k = 0; k < K; ++k) {
+      const float a = __ldg(ar + k);
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+        if (n < N) acc[n] = fmaf(a, sB[n * K + k], acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n < N) C[m * ldc + n] = acc[n];
+  }
+}
+
+// min(M, N) <= 8 with a long reduction (weight gradients of the xyz layer / offset head):
+// out(w, s) = sum_k Wd(w, k) * Sm(s, k), threads over the wide index w, k split across CTAs.
+__global__ void __launch_bounds__(256)
+skinny_reduce_kernel(const float* __restrict__ Wd, long long sww, long long swk, const float* __restrict__ Sm, long long sss,
+                     long long ssk, float* __restrict__ C, long long cw, long long cs, int W, int S, int K, int kchunk) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k0 = blockIdx.y * kchunk, k1 = min(K, k0 + kchunk);
+  if (w >= W) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = k0; k < k1; ++k) {
+    const float a = __ldg(Wd + (long long)w * sww + (long long)k * swk);
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      if (s < S) acc[s] = fmaf(a, __ldg(Sm + (long long)s * sss + (long long)k * ssk), acc[s]);
+  }
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+    if (s < S) atomicAdd(C + (long long)w * cw + (long long)s * cs, acc[s]);
+}
+
+static int gemm_skinny(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk, const float* bias,
+                       float* c, int64_t ldc, int M, int N, int K, cudaStream_t stream, bool* handled) {
+  *handled = true;
+  if (K <= 8 && (size_t)(K + 1) * N * sizeof(float) <= 40 * 1024) {
+    ProfScope ps(KC_GEMM, 2.0 * M * (double)N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N), stream);
+    const int grid = (int)min((long long)num_sms() * 8, ((long long)M + 7) / 8);
+    skinny_k_kernel<<<grid, 256, (size_t)(K + 1) * N * sizeof(float), stream>>>(a, sam, sak, b, sbn, sbk, bias, c, ldc, M, N, K);
+    SUG_LAUNCH_CHECK();
+    return 0;
+  }
+  if (N <= 8 && sak == 1 && K <= 2048 && M >= 4096) {
+    ProfScope ps(KC_GEMM, 2.0 * M * (double)N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N), stream);
+    const int grid = (int)min((long long)num_sms() * 8, ((long long)M + 255) / 256);
+    skinny_n_kernel<<<grid, 256, (size_t)N * K * sizeof(float), stream>>>(a, sam, b, sbn, sbk, bias, c, ldc, M, N, K);
+    SUG_LAUNCH_CHECK();
+    return 0;
+  }
+  if ((N <= 8 || M <= 8) && K >= 4096 && bias == nullptr && max(M, N) <= 4096) {
+    ProfScope ps(KC_GEMM, 2.0 * M * (double)N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N), stream);
+    SUG_CUDA(cudaMemset2DAsync(c, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
+    const bool wide_is_m = N <= 8;
+    const int W = wide_is_m ? M : N, S = wide_is_m ? N : M;
+    const int gx = cdiv(W, 256);
+    int splits = max(1, min(cdiv(K, 256), (4 * num_sms()) / gx));
+    const int kchunk = cdiv(K, splits);
+    splits = cdiv(K, kchunk);
+    if (wide_is_m)
+      skinny_reduce_kernel<<<dim3(gx, splits), 256, 0, stream>>>(a, sam, sak, b, sbn, sbk, c, ldc, 1, W, S, K, kchunk);
+    else
+      skinny_reduce_kernel<<<dim3(gx, splits), 256, 0, stream>>>(b, sbn, sbk, a, sam, sak, c, 1, ldc, W, S, K, kchunk);
+    SUG_LAUNCH_CHECK();
+    return 0;
+  }
+  *handled = false;
+  return 0;
+}
+
 // Dispatcher used by every entry point: the tcgen05 3xTF32 kernel whenever the operands satisfy
 // the TMA constraints (unit stride on one axis, 16 B aligned base, leading dimension % 4 == 0) and
 // the reduction is long enough to feed the tensor core; the CUDA-core kernel otherwise (xyz layers
@@ -151,6 +280,11 @@ int gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t s
     else return false;
     return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (*ld % 4) == 0 && *ld > 0;
   };
+  if (!accumulate) {
+    bool handled = false;
+    SUG_TRY(gemm_skinny(a, sam, sak, b, sbn, sbk, bias, c, ldc, M, N, K, stream, &handled));
+    if (handled) return 0;
+  }
   int a_mn = 0, b_mn = 0;
   int64_t lda = 0, ldb = 0;
   if (!accumulate && K >= 16 && N >= 8 && tma_ok(a, sam, sak, &a_mn, &lda) && tma_ok(b, sbn, sbk, &b_mn, &ldb))
