@@ -331,7 +331,7 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
   extern __shared__ __align__(16) float smem_f[];
   float* As = smem_f;                                        // [N][CH]
   int* widx = reinterpret_cast<int*>(smem_f + (size_t)N * CH);  // [16 warps][PPW * k]
-  __shared__ double red[512][8];                             // stats partials per thread
+  __shared__ double red[16][Q][8];                           // stats partials per (warp, quad)
   const int c0 = blockIdx.x * CH;
   const int b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -429,19 +429,29 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
     }
   }
   if (TRAIN) {
-    // thread t owns quad (t % Q) in both phases (512 % Q == 0 and 32 % Q == 0)
+    // thread t owns quad (t % Q) in both phases (512 % Q == 0 and 32 % Q == 0): fold the lanes of
+    // a warp that share a quad with shuffles, then the 16 warps through shared memory
+    double v[8];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      red[tid][u] = ds[u];
-      red[tid][4 + u] = dq[u] + dsq[u];
+      v[u] = ds[u];
+      v[4 + u] = dq[u] + dsq[u];
+    }
+#pragma unroll
+    for (int o = 16; o >= Q; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
+    if (lane < Q) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) red[warp][lane][u] = v[u];
     }
     __syncthreads();
     if (tid < CH) {
       const int qq = tid >> 2, u = tid & 3;
       double a = 0.0, s2 = 0.0;
-      for (int t = qq; t < 512; t += Q) {
-        a += red[t][u];
-        s2 += red[t][4 + u];
+      for (int w = 0; w < 16; ++w) {
+        a += red[w][qq][u];
+        s2 += red[w][qq][4 + u];
       }
       atomicAdd(&sums[c0 + tid], a);
       atomicAdd(&sums[Cout + c0 + tid], s2);

@@ -150,8 +150,10 @@ class GraphedTrainStep:
         return self
 
     def capture(self):
-        """Record the step into a CUDA graph (call ``warm`` first).  Gradients must be None so that
-        the backward's first write of every ``.grad`` is an assignment inside the graph's pool."""
+        """Record the step into a CUDA graph (call ``warm`` first).  Nothing executes during the
+        capture (the model is not updated), but one set of FPS start indices is drawn.  Gradients
+        must be None so that the backward's first write of every ``.grad`` is an assignment inside
+        the graph's pool."""
         for o in self.opts:
             o.zero_grad(set_to_none=True)
         self._pu.set_fps_start_feed(self._feed)
