@@ -166,6 +166,23 @@ int sug_knn_query(const float* xyz, const float* query, int B, int N, int S, int
                   int32_t* out_idx, sug_stream_t stream);
 int sug_three_nn(const float* xyz, const float* nodes, int B, int N, int M, int k,
                  int32_t* out_idx, sug_stream_t stream);
+/* sug_knn_query without the ordering guarantee: the nsample nearest points as a set (what
+ * adapt_layer_off needs: the group is max-pooled, model_utils.py:121-123). */
+int sug_knn_query_set(const float* xyz, const float* query, int B, int N, int S, int nsample,
+                      int32_t* out_idx, sug_stream_t stream);
+/* index_points(residual_fea, group_idx).max(-1), model_utils.py:122-123, fused: x [B,N,C] point-major,
+ * idx [B,S,K] -> out [B,S,C], arg [B,S,C] (point index of the max).  Backward: dx (zeroed by the
+ * caller) += scatter of g to arg. */
+int sug_group_max_fwd(const float* x, const int32_t* idx, int B, int N, int S, int K, int C, float* out,
+                      int32_t* arg, sug_stream_t stream);
+int sug_group_max_bwd(const float* g, const int32_t* arg, int B, int N, int S, int C, float* dx,
+                      sug_stream_t stream);
+/* torch.sum(index_points(points2, idx) * weight, dim=3), point_utils.py:158-160, fused:
+ * f [B,S,C], idx / w [B,N,K] -> out [B,N,C]; backward accumulates into zeroed df [B,S,C], dw [B,N,K]. */
+int sug_interp_fwd(const float* f, const int32_t* idx, const float* w, int B, int N, int S, int K, int C,
+                   float* out, sug_stream_t stream);
+int sug_interp_bwd(const float* g, const float* f, const int32_t* idx, const float* w, int B, int N, int S,
+                   int K, int C, float* df, float* dw, sug_stream_t stream);
 
 /* Plain fp32 GEMM used inside the entry points above, exported for tests:
  * C[M,N] = A * B^T (+ bias[n]) with A(m,k) = a[m*sam + k*sak], B(n,k) = b[n*sbn + k*sbk]. */

@@ -39,6 +39,11 @@ SIGNATURES = {
     "sug_ball_query": (I, [P, P, I, I, I, F, I, P, P]),
     "sug_knn_query": (I, [P, P, I, I, I, I, P, P]),
     "sug_three_nn": (I, [P, P, I, I, I, I, P, P]),
+    "sug_knn_query_set": (I, [P, P, I, I, I, I, P, P]),
+    "sug_group_max_fwd": (I, [P, P, I, I, I, I, I, P, P, P]),
+    "sug_group_max_bwd": (I, [P, P, I, I, I, I, P, P]),
+    "sug_interp_fwd": (I, [P, P, P, I, I, I, I, I, P, P]),
+    "sug_interp_bwd": (I, [P, P, P, P, I, I, I, I, I, P, P, P]),
     "sug_gemm_f32": (I, [P, L, L, P, L, L, P, P, L, I, I, I, I, P]),
     "sug_gemm_auto_f32": (I, [P, L, L, P, L, L, P, P, L, I, I, I, P]),
     "sug_linear_bn_act_fwd": (I, [P, L, P, P, P, P, P, P, L, I, I, F, F, F, I, P, P, L, P, P, Z, P]),

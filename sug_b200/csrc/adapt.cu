@@ -188,6 +188,145 @@ three_nn_kernel(const float* __restrict__ xyz, const float* __restrict__ nodes, 
   for (int u = 0; u < k; ++u) o[u] = bi[u];
 }
 
+
+// ---- nsample nearest points of every query as a SET (order: increasing point index) ----------------
+// One warp per query, N <= 32*NPL distances in registers as order-preserving uint keys; the
+// nsample-th smallest key is found by a 32-step bitwise search (one warp-wide count per bit), then
+// the selected points are compacted with ballots.  ~20x cheaper than sorting the whole row, and all
+// adapt_layer_off needs (the group is max-pooled, model_utils.py:121-123).
+template <int NPL>
+__global__ void __launch_bounds__(256)
+knn_query_select_kernel(const float* __restrict__ xyz, const float* __restrict__ query, int N, int S, int nsample,
+                        int* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  if (warp >= S) return;
+  const float* xb = xyz + (size_t)b * 3 * N;
+  const float* qb = query + (size_t)b * 3 * S;
+  const float qx = qb[warp], qy = qb[S + warp], qz = qb[2 * S + warp];
+  const float nq = sq3(qx, qy, qz);
+  unsigned u[NPL];
+#pragma unroll
+  for (int t = 0; t < NPL; ++t) {
+    const int i = lane + 32 * t;
+    unsigned key = 0xffffffffu;
+    if (i < N) {
+      const float x = xb[i], y = xb[N + i], z = xb[2 * N + i];
+      const float d = sqdist_expanded(dot3(qx, qy, qz, x, y, z), nq, sq3(x, y, z));
+      const unsigned bits = __float_as_uint(d);
+      key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+    }
+    u[t] = key;
+  }
+  unsigned T = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const unsigned cand = T | (1u << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int t = 0; t < NPL; ++t) cnt += (u[t] < cand) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (cnt < nsample) T = cand;
+  }
+  int c_lt = 0;
+#pragma unroll
+  for (int t = 0; t < NPL; ++t) c_lt += (u[t] < T) ? 1 : 0;
+  c_lt = __reduce_add_sync(0xffffffffu, c_lt);
+  const int need_eq = nsample - c_lt;
+  int* o = out + ((size_t)b * S + warp) * nsample;
+  const unsigned ltmask = (1u << lane) - 1u;
+  int base_lt = 0, seen_eq = 0;
+#pragma unroll
+  for (int t = 0; t < NPL; ++t) {
+    const bool lt = u[t] < T, eq = u[t] == T;
+    const unsigned bl = __ballot_sync(0xffffffffu, lt), be = __ballot_sync(0xffffffffu, eq);
+    if (lt) o[base_lt + __popc(bl & ltmask)] = lane + 32 * t;
+    if (eq) {
+      const int r = seen_eq + __popc(be & ltmask);
+      if (r < need_eq) o[c_lt + r] = lane + 32 * t;
+    }
+    base_lt += __popc(bl);
+    seen_eq += __popc(be);
+  }
+}
+
+// ---- fused gather + max over a group (node features), with the arg for the backward ----------------
+__global__ void __launch_bounds__(256)
+group_max_fwd_kernel(const float* __restrict__ x, const int* __restrict__ idx, int N, int S, int K, int C,
+                     float* __restrict__ out, int* __restrict__ arg) {
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int* ip = idx + ((size_t)b * S + s) * K;
+  const float* xb = x + (size_t)b * N * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float best = -INFINITY;
+    int bj = 0;
+    for (int k = 0; k < K; ++k) {
+      const int j = __ldg(ip + k);
+      const float v = __ldg(xb + (size_t)j * C + c);
+      if (v > best) { best = v; bj = j; }
+    }
+    out[((size_t)b * S + s) * C + c] = best;
+    arg[((size_t)b * S + s) * C + c] = bj;
+  }
+}
+__global__ void __launch_bounds__(256)
+group_max_bwd_kernel(const float* __restrict__ g, const int* __restrict__ arg, int N, int S, int C, float* __restrict__ dx) {
+  const int s = blockIdx.x, b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const size_t o = ((size_t)b * S + s) * C + c;
+    atomicAdd(dx + ((size_t)b * N + arg[o]) * C + c, g[o]);
+  }
+}
+
+// ---- weighted K-neighbour interpolation of node features back to the points -------------------------
+// out[b,n,:] = sum_k w[b,n,k] f[b, idx[b,n,k], :]        (point_utils.py:158-160, upsample_inter)
+__global__ void __launch_bounds__(256)
+interp_fwd_kernel(const float* __restrict__ f, const int* __restrict__ idx, const float* __restrict__ w, int N, int S,
+                  int K, int C, float* __restrict__ out) {
+  extern __shared__ float sf[];  // [S][C]
+  const int b = blockIdx.y;
+  for (int e = threadIdx.x; e < S * C; e += blockDim.x) sf[e] = f[(size_t)b * S * C + e];
+  __syncthreads();
+  const int ppb = blockDim.x / C;  // points per block step (C <= 256 and divides 256)
+  const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  for (int n = blockIdx.x * ppb + pl; n < N; n += gridDim.x * ppb) {
+    const size_t r = (size_t)b * N + n;
+    float o = 0.f;
+    for (int k = 0; k < K; ++k) o = fmaf(__ldg(w + r * K + k), sf[__ldg(idx + r * K + k) * C + c], o);
+    out[r * C + c] = o;
+  }
+}
+// df[b,i,:] += w g ;  dw[b,n,k] = <g[b,n,:], f[b,i_k,:]>
+__global__ void __launch_bounds__(256)
+interp_bwd_kernel(const float* __restrict__ g, const float* __restrict__ f, const int* __restrict__ idx,
+                  const float* __restrict__ w, int N, int S, int K, int C, float* __restrict__ df, float* __restrict__ dw) {
+  extern __shared__ float sm[];  // f [S][C], acc [S][C]
+  float* sf = sm;
+  float* sa = sm + (size_t)S * C;
+  const int b = blockIdx.y;
+  for (int e = threadIdx.x; e < S * C; e += blockDim.x) {
+    sf[e] = f[(size_t)b * S * C + e];
+    sa[e] = 0.f;
+  }
+  __syncthreads();
+  const int ppb = blockDim.x / C;
+  const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  for (int n = blockIdx.x * ppb + pl; n < N; n += gridDim.x * ppb) {
+    const size_t r = (size_t)b * N + n;
+    const float gv = __ldg(g + r * C + c);
+    for (int k = 0; k < K; ++k) {
+      const int i = __ldg(idx + r * K + k);
+      atomicAdd(&sa[i * C + c], __ldg(w + r * K + k) * gv);
+      // dw: reduce gv * f over the C threads of this point (C is a multiple of 32)
+      float d = gv * sf[i * C + c];
+      d = warp_sum(d);
+      if ((threadIdx.x & 31) == 0) atomicAdd(dw + r * K + k, d);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < S * C; e += blockDim.x) atomicAdd(df + (size_t)b * S * C + e, sa[e]);
+}
+
 }  // namespace sug
 
 using namespace sug;
@@ -218,6 +357,56 @@ extern "C" int sug_ball_query(const float* xyz, const float* query, int B, int N
   dim3 grid(cdiv((long long)S * 32, 256), B);
   ProfScope ps(KC_ADAPT, 0, 0, (cudaStream_t)stream);
   ball_query_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyz, query, N, S, r2, nsample, out_idx);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_knn_query_set(const float* xyz, const float* query, int B, int N, int S, int nsample, int32_t* out_idx,
+                                 sug_stream_t stream) {
+  SUG_CHECK_ARG(xyz && query && out_idx, "knn_query_set: null pointer");
+  SUG_CHECK_ARG(B > 0 && N > 0 && S > 0 && nsample > 0 && nsample <= N, "knn_query_set: bad shape");
+  if (N > 2048) return sug_knn_query(xyz, query, B, N, S, nsample, out_idx, stream);
+  dim3 grid(cdiv((long long)S * 32, 256), B);
+  ProfScope ps(KC_ADAPT, 0, 0, (cudaStream_t)stream);
+  if (N <= 1024) knn_query_select_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(xyz, query, N, S, nsample, out_idx);
+  else knn_query_select_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(xyz, query, N, S, nsample, out_idx);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_group_max_fwd(const float* x, const int32_t* idx, int B, int N, int S, int K, int C, float* out,
+                                 int32_t* arg, sug_stream_t stream) {
+  SUG_CHECK_ARG(x && idx && out && arg && B > 0 && N > 0 && S > 0 && K > 0 && C > 0, "group_max_fwd: bad argument");
+  ProfScope ps(KC_ADAPT, 0, 4.0 * B * S * ((double)K * C + 2.0 * C), (cudaStream_t)stream);
+  group_max_fwd_kernel<<<dim3(S, B), C < 256 ? ((C + 31) / 32) * 32 : 256, 0, (cudaStream_t)stream>>>(x, idx, N, S, K, C, out, arg);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sug_group_max_bwd(const float* g, const int32_t* arg, int B, int N, int S, int C, float* dx,
+                                 sug_stream_t stream) {
+  SUG_CHECK_ARG(g && arg && dx && B > 0 && N > 0 && S > 0 && C > 0, "group_max_bwd: bad argument");
+  ProfScope ps(KC_ADAPT, 0, 12.0 * B * S * C, (cudaStream_t)stream);
+  group_max_bwd_kernel<<<dim3(S, B), C < 256 ? ((C + 31) / 32) * 32 : 256, 0, (cudaStream_t)stream>>>(g, arg, N, S, C, dx);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_interp_fwd(const float* f, const int32_t* idx, const float* w, int B, int N, int S, int K, int C,
+                              float* out, sug_stream_t stream) {
+  SUG_CHECK_ARG(f && idx && w && out && B > 0 && N > 0 && S > 0 && K > 0, "interp_fwd: bad argument");
+  SUG_CHECK_ARG(C >= 32 && C <= 256 && 256 % C == 0 && (size_t)S * C * 4 <= 48 * 1024, "interp_fwd: C=%d S=%d unsupported", C, S);
+  ProfScope ps(KC_ADAPT, 2.0 * B * N * K * C, 4.0 * B * N * (C + 2.0 * K), (cudaStream_t)stream);
+  interp_fwd_kernel<<<dim3(8, B), 256, (size_t)S * C * 4, (cudaStream_t)stream>>>(f, idx, w, N, S, K, C, out);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+// df [B,S,C] and dw [B,N,K] must be zero on entry (accumulated with atomics).
+extern "C" int sug_interp_bwd(const float* g, const float* f, const int32_t* idx, const float* w, int B, int N, int S, int K,
+                              int C, float* df, float* dw, sug_stream_t stream) {
+  SUG_CHECK_ARG(g && f && idx && w && df && dw && B > 0 && N > 0 && S > 0 && K > 0, "interp_bwd: bad argument");
+  SUG_CHECK_ARG(C >= 32 && C <= 256 && 256 % C == 0 && (size_t)S * C * 8 <= 48 * 1024, "interp_bwd: C=%d S=%d unsupported", C, S);
+  ProfScope ps(KC_ADAPT, 4.0 * B * N * K * C, 4.0 * B * N * (C + 3.0 * K), (cudaStream_t)stream);
+  interp_bwd_kernel<<<dim3(8, B), 256, (size_t)S * C * 8, (cudaStream_t)stream>>>(g, f, idx, w, N, S, K, C, df, dw);
   SUG_LAUNCH_CHECK();
   return 0;
 }

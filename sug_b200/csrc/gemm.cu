@@ -187,22 +187,36 @@ skinny_k_kernel(const float* __restrict__ A, long long sam, long long sak, const
 __global__ void __launch_bounds__(256)
 skinny_n_kernel(const float* __restrict__ A, long long sam, const float* __restrict__ Bm, long long sbn, long long sbk,
                 const float* __restrict__ bias, float* __restrict__ C, long long ldc, int M, int N, int K) {
-  extern __shared__ float sB[];  // [N][K]
+  extern __shared__ __align__(16) float sB[];  // [N][K]
   for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
     int k = e % K, n = e / K;
     sB[n * K + k] = __ldg(Bm + (long long)n * sbn + (long long)k * sbk);
   }
   __syncthreads();
+  const bool vec = (K % 4 == 0) && (sam % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
   for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
     float acc[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n) acc[n] = (bias && n < N) ? __ldg(bias + n) : 0.f;
     const float* ar = A + m * sam;
-    for (int k = 0; k < K; ++k) {
-      const float a = __ldg(ar + k);
+    if (vec) {
+      for (int k = 0; k < K; k += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(ar + k));
 #pragma unroll
-      for (int n = 0; n < 8; ++n)
-        if (n < N) acc[n] = fmaf(a, sB[n * K + k], acc[n]);
+        for (int n = 0; n < 8; ++n) {
+          if (n < N) {
+            const float4 w = *reinterpret_cast<const float4*>(sB + n * K + k);
+            acc[n] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[n]))));
+          }
+        }
+      }
+    } else {
+      for (int k = 0; k < K; ++k) {
+        const float a = __ldg(ar + k);
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+          if (n < N) acc[n] = fmaf(a, sB[n * K + k], acc[n]);
+      }
     }
 #pragma unroll
     for (int n = 0; n < 8; ++n)
@@ -211,23 +225,39 @@ skinny_n_kernel(const float* __restrict__ A, long long sam, const float* __restr
 }
 
 // min(M, N) <= 8 with a long reduction (weight gradients of the xyz layer / offset head):
-// out(w, s) = sum_k Wd(w, k) * Sm(s, k), threads over the wide index w, k split across CTAs.
+// out(w, s) = sum_k Wd(w, k) * Sm(s, k).  A block covers TW wide indices x (256 / TW) interleaved
+// k-slices, reduces the slices through shared memory and issues one atomic per output and block.
 __global__ void __launch_bounds__(256)
 skinny_reduce_kernel(const float* __restrict__ Wd, long long sww, long long swk, const float* __restrict__ Sm, long long sss,
-                     long long ssk, float* __restrict__ C, long long cw, long long cs, int W, int S, int K, int kchunk) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+                     long long ssk, float* __restrict__ C, long long cw, long long cs, int W, int S, int K, int kchunk,
+                     int TW) {
+  __shared__ float red[256][8];
+  const int KS = 256 / TW;
+  const int wl = threadIdx.x % TW, ks = threadIdx.x / TW;
+  const int w = blockIdx.x * TW + wl;
   const int k0 = blockIdx.y * kchunk, k1 = min(K, k0 + kchunk);
-  if (w >= W) return;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int k = k0; k < k1; ++k) {
-    const float a = __ldg(Wd + (long long)w * sww + (long long)k * swk);
+  if (w < W) {
+    for (int k = k0 + ks; k < k1; k += KS) {
+      const float a = __ldg(Wd + (long long)w * sww + (long long)k * swk);
 #pragma unroll
-    for (int s = 0; s < 8; ++s)
-      if (s < S) acc[s] = fmaf(a, __ldg(Sm + (long long)s * sss + (long long)k * ssk), acc[s]);
+      for (int s = 0; s < 8; ++s)
+        if (s < S) acc[s] = fmaf(a, __ldg(Sm + (long long)s * sss + (long long)k * ssk), acc[s]);
+    }
   }
 #pragma unroll
-  for (int s = 0; s < 8; ++s)
-    if (s < S) atomicAdd(C + (long long)w * cw + (long long)s * cs, acc[s]);
+  for (int s = 0; s < 8; ++s) red[threadIdx.x][s] = acc[s];
+  __syncthreads();
+  if (ks == 0 && w < W) {
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      if (s < S) {
+        float t = 0.f;
+        for (int r = 0; r < KS; ++r) t += red[r * TW + wl][s];
+        atomicAdd(C + (long long)w * cw + (long long)s * cs, t);
+      }
+    }
+  }
 }
 
 static int gemm_skinny(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk, const float* bias,
@@ -252,14 +282,16 @@ static int gemm_skinny(const float* a, int64_t sam, int64_t sak, const float* b,
     SUG_CUDA(cudaMemset2DAsync(c, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
     const bool wide_is_m = N <= 8;
     const int W = wide_is_m ? M : N, S = wide_is_m ? N : M;
-    const int gx = cdiv(W, 256);
-    int splits = max(1, min(cdiv(K, 256), (4 * num_sms()) / gx));
+    int TW = 32;
+    while (TW < W && TW < 256) TW <<= 1;
+    const int gx = cdiv(W, TW);
+    int splits = max(1, min(cdiv(K, 2048), (2 * num_sms()) / gx));
     const int kchunk = cdiv(K, splits);
     splits = cdiv(K, kchunk);
     if (wide_is_m)
-      skinny_reduce_kernel<<<dim3(gx, splits), 256, 0, stream>>>(a, sam, sak, b, sbn, sbk, c, ldc, 1, W, S, K, kchunk);
+      skinny_reduce_kernel<<<dim3(gx, splits), 256, 0, stream>>>(a, sam, sak, b, sbn, sbk, c, ldc, 1, W, S, K, kchunk, TW);
     else
-      skinny_reduce_kernel<<<dim3(gx, splits), 256, 0, stream>>>(b, sbn, sbk, a, sam, sak, c, 1, ldc, W, S, K, kchunk);
+      skinny_reduce_kernel<<<dim3(gx, splits), 256, 0, stream>>>(b, sbn, sbk, a, sam, sak, c, 1, ldc, W, S, K, kchunk, TW);
     SUG_LAUNCH_CHECK();
     return 0;
   }

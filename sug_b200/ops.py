@@ -443,15 +443,89 @@ def ball_query(xyz, query, radius: float, nsample: int) -> torch.Tensor:
     return out
 
 
-def knn_query(xyz, query, nsample: int) -> torch.Tensor:
+def knn_query(xyz, query, nsample: int, ordered: bool = True) -> torch.Tensor:
+    """nsample nearest points of every query: ascending by distance (``ordered``) or as a set."""
     xyz, query = _xyz(xyz), _xyz(query)
     B, _, N = xyz.shape
     S = query.shape[2]
     out = torch.empty(B, S, nsample, dtype=torch.int32, device=xyz.device)
     lib = _lib.load()
+    fn = lib.sug_knn_query if ordered else lib.sug_knn_query_set
     with torch.cuda.device(xyz.device):
-        _lib.check(lib.sug_knn_query(_ptr(xyz), _ptr(query), B, N, S, nsample, _ptr(out), _stream()), "sug_knn_query")
+        _lib.check(fn(_ptr(xyz), _ptr(query), B, N, S, nsample, _ptr(out), _stream()), "sug_knn_query")
     return out
+
+
+class _GroupMaxFn(torch.autograd.Function):
+    """x [B,N,C] point-major, idx int32 [B,S,K] -> max over the K gathered rows, [B,S,C]."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        x = x.float().contiguous()
+        B, N, C = x.shape
+        _, S, K = idx.shape
+        out = torch.empty(B, S, C, dtype=torch.float32, device=x.device)
+        arg = torch.empty(B, S, C, dtype=torch.int32, device=x.device)
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.sug_group_max_fwd(_ptr(x), _ptr(idx), B, N, S, K, C, _ptr(out), _ptr(arg), _stream()),
+                       "sug_group_max_fwd")
+        ctx.save_for_backward(arg)
+        ctx.shape = (B, N, S, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        B, N, S, C = ctx.shape
+        g = g.float().contiguous()
+        dx = torch.zeros(B, N, C, dtype=torch.float32, device=g.device)
+        lib = _lib.load()
+        with torch.cuda.device(g.device):
+            _lib.check(lib.sug_group_max_bwd(_ptr(g), _ptr(arg), B, N, S, C, _ptr(dx), _stream()), "sug_group_max_bwd")
+        return dx, None
+
+
+def group_max(x, idx):
+    _need_cuda(x, idx)
+    return _GroupMaxFn.apply(x, idx.int().contiguous())
+
+
+class _InterpFn(torch.autograd.Function):
+    """f [B,S,C], idx int32 [B,N,K], w [B,N,K] -> sum_k w f[idx]  [B,N,C]."""
+
+    @staticmethod
+    def forward(ctx, f, idx, w):
+        f = f.float().contiguous()
+        w = w.float().contiguous()
+        B, S, C = f.shape
+        _, N, K = idx.shape
+        out = torch.empty(B, N, C, dtype=torch.float32, device=f.device)
+        lib = _lib.load()
+        with torch.cuda.device(f.device):
+            _lib.check(lib.sug_interp_fwd(_ptr(f), _ptr(idx), _ptr(w), B, N, S, K, C, _ptr(out), _stream()),
+                       "sug_interp_fwd")
+        ctx.save_for_backward(f, idx, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f, idx, w = ctx.saved_tensors
+        B, S, C = f.shape
+        _, N, K = idx.shape
+        g = g.float().contiguous()
+        df = torch.zeros_like(f)
+        dw = torch.zeros_like(w)
+        lib = _lib.load()
+        with torch.cuda.device(g.device):
+            _lib.check(lib.sug_interp_bwd(_ptr(g), _ptr(f), _ptr(idx), _ptr(w), B, N, S, K, C, _ptr(df), _ptr(dw),
+                                          _stream()), "sug_interp_bwd")
+        return df, None, dw
+
+
+def interpolate(f, idx, w):
+    _need_cuda(f, idx, w)
+    return _InterpFn.apply(f, idx.int().contiguous(), w)
 
 
 def three_nn(xyz, nodes, k: int = 3) -> torch.Tensor:
