@@ -238,7 +238,22 @@ skinny_reduce_kernel(const float* __restrict__ Wd, long long sww, long long swk,
   const int k0 = blockIdx.y * kchunk, k1 = min(K, k0 + kchunk);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (w < W) {
-    for (int k = k0 + ks; k < k1; k += KS) {
+    // the operands stream from HBM exactly once: keep 4 independent rows in flight per thread
+    int k = k0 + ks;
+    for (; k + 3 * KS < k1; k += 4 * KS) {
+      float a[4], sv[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = __ldg(Wd + (long long)w * sww + (long long)(k + u * KS) * swk);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) sv[u][s] = s < S ? __ldg(Sm + (long long)s * sss + (long long)(k + u * KS) * ssk) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) acc[s] = fmaf(a[u], sv[u][s], acc[s]);
+    }
+    for (; k < k1; k += KS) {
       const float a = __ldg(Wd + (long long)w * sww + (long long)k * swk);
 #pragma unroll
       for (int s = 0; s < 8; ++s)
@@ -285,7 +300,7 @@ static int gemm_skinny(const float* a, int64_t sam, int64_t sak, const float* b,
     int TW = 32;
     while (TW < W && TW < 256) TW <<= 1;
     const int gx = cdiv(W, TW);
-    int splits = max(1, min(cdiv(K, 2048), (2 * num_sms()) / gx));
+    int splits = max(1, min(cdiv(K, 256), (2 * num_sms()) / gx));
     const int kchunk = cdiv(K, splits);
     splits = cdiv(K, kchunk);
     if (wide_is_m)
