@@ -164,6 +164,12 @@ def main():
 
     from sug_b200 import Model, _lib, dist as sdist, model_utils, step, synth
     import torch.distributed as tdist
+    trace_on = os.environ.get("SUG_BENCH_TRACE") == "1"
+
+    def trace(msg):
+        if trace_on:
+            print(f"[bench rank {os.environ.get('RANK', '0')}] {time.strftime('%H:%M:%S')} {msg}", file=sys.stderr, flush=True)
+    trace("init process group")
     rank, world, local = sdist.init_from_env()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -204,6 +210,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up (untimed) + one instrumented step to find the dominant kernel class --------------
+    trace("eager warm-up")
     for i in range(args.warmup):
         run_step(*dev_batches[i % len(dev_batches)])
     _lib.prof_reset(mask=0xFFFFFFFF)
@@ -216,6 +223,7 @@ def main():
     prof_mask = 0xFFFFFFFF if args.profile_all else (1 << prof1[dom]["index"])
     _lib.prof_reset(mask=prof_mask)
     graphed, mode = None, "eager"
+    trace(f"dominant class {dom}; building the graphed step")
     if not args.no_graph:
         try:
             for o in opts:
@@ -236,6 +244,7 @@ def main():
             run_step(*dev_batches[i % len(dev_batches)])
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------------
+    trace(f"mode {mode}; timed region 1")
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -260,6 +269,7 @@ def main():
     if graphed is None:
         _lib.prof_reset(mask=0)
     host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    trace("timed region 2 (e2e)")
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -278,6 +288,7 @@ def main():
     ms_e2e = float(t.item())
     e2e_value = clouds_per_step * args.steps / (ms_e2e / 1e3)
 
+    trace("done timing")
     if rank != 0:
         if world > 1:
             tdist.destroy_process_group()

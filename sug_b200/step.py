@@ -112,17 +112,21 @@ class GraphedTrainStep:
         self.graph = None
         self.out = None
 
-    def _body(self):
+    def _fwd_bwd(self):
         self._call = 0
         if self._alpha0 is not None:
             self.crit.alpha = self._alpha0
         out = sug_losses(self.model, self.data, self.label, self.data_t, self.label_t, self.crit, self.cfg, self.mmd_fn)
         out["loss"].backward()
+        return {k: v.detach() for k, v in out.items()}
+
+    def _body(self):
+        out = self._fwd_bwd()
         if self.hook is not None:
             self.hook(self.model)
         for o in self.opts:
             o.step()
-        return {k: v.detach() for k, v in out.items()}
+        return out
 
     def _draw_fps(self):
         for i in range(4):  # same CPU-RNG consumption as four eager forwards
@@ -161,8 +165,29 @@ class GraphedTrainStep:
             self._draw_fps()
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.out = self._body()
+            if self.hook is None:
+                with torch.cuda.graph(self.graph):
+                    self.out = self._body()
+            else:
+                # data parallel: the collective stays OUTSIDE the graphs (graph A: forwards + backward +
+                # flatten; eager NCCL all-reduce of the flat bucket; graph B: average, unflatten, Adam)
+                import torch.distributed as tdist
+                self._tdist = tdist
+                world = tdist.get_world_size()
+                with torch.cuda.graph(self.graph):
+                    self.out = self._fwd_bwd()
+                    self._grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+                    self._flat = torch.cat([g.reshape(-1) for g in self._grads])
+                self.graph_b = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_b, pool=self.graph.pool()):
+                    self._flat.div_(world)
+                    off, views = 0, []
+                    for g in self._grads:
+                        views.append(self._flat[off:off + g.numel()].view_as(g))
+                        off += g.numel()
+                    torch._foreach_copy_(self._grads, views)
+                    for o in self.opts:
+                        o.step()
         finally:
             self._pu.set_fps_start_feed(None)
         torch.cuda.synchronize()
@@ -176,4 +201,7 @@ class GraphedTrainStep:
         self.label_t.copy_(label_t, non_blocking=True)
         self._draw_fps()
         self.graph.replay()
+        if self.hook is not None:
+            self._tdist.all_reduce(self._flat)
+            self.graph_b.replay()
         return self.out
