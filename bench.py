@@ -128,13 +128,13 @@ def cpu_step_time(batch: int, steps: int, warmup: int):
         out["loss"].backward()
         opt.step()
         opt.zero_grad()
-        float(out["loss"])
+        float(out["loss"].detach())
         if it >= warmup:
             ts.append(time.perf_counter() - t0)
     return sum(ts) / len(ts), torch.get_num_threads()
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit):
     if rank != 0:
         return
     bs = 4
@@ -149,15 +149,30 @@ def run_reference(args, rank):
                              "sample": f"SUG step at {bs}+{bs} clouds x {N_POINTS} pts (batch reduced from 64+64), "
                                        f"oracle/sug_oracle.py on {cores} host threads"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
+    # stdout carries exactly one JSON line: anything libraries print (e.g. NCCL's version banner) goes
+    # to stderr instead
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+    try:
+        _main(args, rank, emit)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+
+
+def _main(args, rank, emit):
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, emit)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
@@ -224,7 +239,7 @@ def main():
     _lib.prof_reset(mask=prof_mask)
     graphed, mode = None, "eager"
     trace(f"dominant class {dom}; building the graphed step")
-    if not args.no_graph:
+    if not args.no_graph and mmd_fn is None:  # a collective inside the forward (global MMD) is not captured
         try:
             for o in opts:
                 o.zero_grad(set_to_none=True)
@@ -333,7 +348,7 @@ def main():
         line["cpu_baseline"] = {"value": 2 * bs / sec, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"1 SUG step at {bs}+{bs} clouds x {N_POINTS} pts (batch reduced from 64+64), "
                                           f"oracle/sug_oracle.py on {cores} host threads"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         tdist.destroy_process_group()
 

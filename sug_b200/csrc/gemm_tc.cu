@@ -29,9 +29,10 @@ struct TcCfg {
   static constexpr int A_BYTES = TBM * TBK * 4;  // 16 KB
   static constexpr int B_BYTES = BN * TBK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_BYTES = 4 * 2 * 4096;  // per epilogue warp: two 32x32 fp32 staging tiles
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct TcArgs {
@@ -41,16 +42,19 @@ struct TcArgs {
   int M, N, K;
   int tiles_m, tiles_n, ksplits, kb_per_split;
   int epi;
+  int tma_store;  // epilogue through shared memory + cp.async.bulk.tensor (needs an aligned C)
 };
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, TcArgs p) {
   using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+  uint8_t* epi_smem = smem + S * Cfg::STAGE_BYTES;  // 1024 B aligned (stage sizes are multiples of 1024)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* full = bars;            // [S]  TMA -> split
   uint64_t* ready = bars + S;       // [S]  split -> MMA
   uint64_t* empty = bars + 2 * S;   // [S]  MMA -> TMA
@@ -65,6 +69,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&ready[s], 128);
@@ -184,36 +189,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================== epilogue ===========================================
     const int lg = warp & 3;  // TMEM lane group this warp may access
     uint32_t tile_it = 0;
+    uint8_t* stg = epi_smem + (warp - 6) * 8192;  // this warp's two 32x32 staging tiles
+    uint32_t chunk_it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
       const int nt = t % p.tiles_n, mt = (t / p.tiles_n) % p.tiles_m;
       const int ab = tile_it & 1;
       mbar_wait(&tfull[ab], (tile_it >> 1) & 1);
       tc_fence_after();
       const int row = mt * TBM + lg * 32 + lane;
-      float* crow = p.C + (long long)row * p.ldc;
-      const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+      if (p.tma_store) {
+        // TMEM -> registers -> 128B-swizzled staging tile -> bulk tensor store (or reduce-add for
+        // split-K): every global write is a full, coalesced 128 B row segment, tails are clipped by TMA
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + ab * BN + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = nt * BN + c * 32;
-        if (row < p.M && col0 < p.N) {
+        for (int c = 0; c < BN / 32; ++c, ++chunk_it) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + ab * BN + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = nt * BN + c * 32;
           if (p.bias != nullptr && p.epi == EPI_STORE) {
 #pragma unroll
             for (int q = 0; q < 32; ++q)
               if (col0 + q < p.N) v[q] += __ldg(p.bias + col0 + q);
           }
-          if (p.epi == EPI_STORE && vec_ok && col0 + 32 <= p.N) {
+          uint8_t* buf = stg + (chunk_it & 1) * 4096;
+          if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago has read this buffer
+          __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(crow + col0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          } else {
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && col0 < p.N && mt * TBM + lg * 32 < p.M) {
+            if (p.epi == EPI_ATOMIC) tma_reduce_add_2d(&tmC, buf, col0, mt * TBM + lg * 32);
+            else tma_store_2d(&tmC, buf, col0, mt * TBM + lg * 32);
+          }
+          if (lane == 0) tma_store_commit();
+        }
+      } else {
+        float* crow = p.C + (long long)row * p.ldc;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + ab * BN + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = nt * BN + c * 32;
+          if (row < p.M && col0 < p.N) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
               if (col0 + q < p.N) {
-                if (p.epi == EPI_ATOMIC) atomicAdd(crow + col0 + q, v[q]);
-                else crow[col0 + q] = v[q];
+                float o = v[q];
+                if (p.bias != nullptr && p.epi == EPI_STORE) o += __ldg(p.bias + col0 + q);
+                if (p.epi == EPI_ATOMIC) atomicAdd(crow + col0 + q, o);
+                else crow[col0 + q] = o;
               }
             }
           }
@@ -222,6 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(&tempty[ab]);
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -276,7 +305,8 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t r
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, int grid, cudaStream_t stream) {
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcArgs& args, int grid,
+                     cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -284,7 +314,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
                                   Cfg::SMEM_BYTES));
     configured = true;
   }
-  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, args);
+  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, args);
   SUG_LAUNCH_CHECK();
   return 0;
 }
@@ -294,7 +324,10 @@ int gemm_tc_f32(const float* a, int64_t lda, int a_mn, const float* b, int64_t l
                 int64_t ldc, int M, int N, int K, cudaStream_t stream) {
   SUG_CHECK_ARG(M > 0 && N > 0 && K > 0 && a && b && c, "gemm_tc: bad problem M=%d N=%d K=%d", M, N, K);
   const int BN = (N <= 64) ? 64 : 128;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
+  const bool c_tma = (reinterpret_cast<uintptr_t>(c) & 15) == 0 && ldc % 4 == 0;
+  if (c_tma) SUG_TRY(make_tmap_2d(&tmC, c, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32));
+  else tmC = CUtensorMap();
   if (!a_mn) SUG_TRY(make_tmap_2d(&tmA, a, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBM));
   else SUG_TRY(make_tmap_2d(&tmA, a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, TBK, true));
   if (!b_mn) SUG_TRY(make_tmap_2d(&tmB, b, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)BN));
@@ -313,6 +346,7 @@ int gemm_tc_f32(const float* a, int64_t lda, int a_mn, const float* b, int64_t l
   args.kb_per_split = cdiv(kb_total, splits);
   args.ksplits = cdiv(kb_total, args.kb_per_split);
   args.epi = args.ksplits > 1 ? EPI_ATOMIC : EPI_STORE;
+  args.tma_store = c_tma ? 1 : 0;
   if (args.epi == EPI_ATOMIC) {
     SUG_CHECK_ARG(bias == nullptr, "gemm_tc: bias with split-K is not supported");
     SUG_CUDA(cudaMemset2DAsync(c, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
@@ -321,10 +355,10 @@ int gemm_tc_f32(const float* a, int64_t lda, int a_mn, const float* b, int64_t l
   ProfScope ps(KC_GEMM_TC, 2.0 * M * (double)N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N), stream);
 #define SUG_TC(BN_)                                                                     \
   do {                                                                                  \
-    if (!a_mn && !b_mn) return launch_tc<BN_, false, false>(tmA, tmB, args, grid, stream); \
-    if (!a_mn && b_mn) return launch_tc<BN_, false, true>(tmA, tmB, args, grid, stream);   \
-    if (a_mn && !b_mn) return launch_tc<BN_, true, false>(tmA, tmB, args, grid, stream);   \
-    return launch_tc<BN_, true, true>(tmA, tmB, args, grid, stream);                       \
+    if (!a_mn && !b_mn) return launch_tc<BN_, false, false>(tmA, tmB, tmC, args, grid, stream); \
+    if (!a_mn && b_mn) return launch_tc<BN_, false, true>(tmA, tmB, tmC, args, grid, stream);   \
+    if (a_mn && !b_mn) return launch_tc<BN_, true, false>(tmA, tmB, tmC, args, grid, stream);   \
+    return launch_tc<BN_, true, true>(tmA, tmB, tmC, args, grid, stream);                       \
   } while (0)
   if (BN == 64) SUG_TC(64);
   SUG_TC(128);
