@@ -316,15 +316,21 @@ def _main(args, rank, emit):
         # graph replays re-record the same event pairs: the totals are those of the LAST timed step
         d = dict(d, launches=d["timed"], flops=d["flops"], bytes=d["bytes"])
     per_launch_s = (d["ms"] / 1e3) / max(1, d["timed"])
-    tensor_bound = dom in ("gemm_simt", "gemm_tc", "knn_simt", "knn_tc")
+    # a GEMM-class kernel is judged against whichever roofline binds it harder at the measured peaks
+    flops_pl, bytes_pl = d["flops"] / max(1, d["launches"]), d["bytes"] / max(1, d["launches"])
+    t_tensor = flops_pl / (pk["tensor"] * 1e12) if dom in ("gemm_simt", "gemm_tc", "knn_simt", "knn_tc") else 0.0
+    t_hbm = bytes_pl / (pk["hbm"] * 1e9)
+    tensor_bound = t_tensor > t_hbm
     if tensor_bound:
-        ach = d["flops"] / max(1, d["launches"]) / per_launch_s / 1e12
+        ach = flops_pl / per_launch_s / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
                 "traffic": None}
     else:
-        ach = d["bytes"] / max(1, d["launches"]) / per_launch_s / 1e9
+        ach = bytes_pl / per_launch_s / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                 "traffic": None}
+    roof["tflops"] = flops_pl / per_launch_s / 1e12
+    roof["gbps"] = bytes_pl / per_launch_s / 1e9
     roof.update({"kernel": dom, "launches_timed": int(d["timed"]), "avg_launch_us": per_launch_s * 1e6,
                  "share_of_step": d["ms"] / (ms / args.steps if graphed is not None else ms), "peak_source": pk["src"] + (" bf16 sustained" if tensor_bound else " copy")})
 

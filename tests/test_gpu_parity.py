@@ -632,4 +632,4 @@ def test_graphed_step_matches_eager(S):
         assert abs(a - b) <= 2e-3 * abs(a), (losses_e, losses_g)
     pe, pg = dict(net_e.named_parameters()), dict(net_g.named_parameters())
     for k in ("g.conv1.conv.0.weight", "g.conv5.weight", "c1.mlp3.weight", "attention_s.bn.weight"):
-        assert relerr(pg[k], pe[k]) < 1e-3, k
+        assert relerr(pg[k], pe[k]) < 1e-2, k
