@@ -24,14 +24,23 @@ constexpr int TC_THREADS = 320;
 
 enum { EPI_STORE = 0, EPI_ATOMIC = 1 };
 
-template <int BN>
+// A_TS: the A operand (K-major) is staged in TMEM (hi and lo written by the split warps with
+// tcgen05.st), so shared memory only holds the raw A tile (TMA destination) and B hi / lo.  A 128x128x8
+// tf32 MMA with both operands in shared memory reads 8 KB per 64 cycles = the whole 128 B/clk of an SM;
+// with three products per k-step the SS form is shared-memory-bandwidth bound, the TS form is not.
+template <int BN, bool A_TS>
 struct TcCfg {
   static constexpr int A_BYTES = TBM * TBK * 4;  // 16 KB
   static constexpr int B_BYTES = BN * TBK * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+  static constexpr int A_SMEM = A_TS ? A_BYTES : 2 * A_BYTES;
+  static constexpr int STAGE_BYTES = A_SMEM + 2 * B_BYTES;
+  static constexpr int STAGES = A_TS ? ((2 * BN + 4 * 64 <= 512 && 4 * STAGE_BYTES <= 192 * 1024) ? 4 : 3)
+                                     : (192 * 1024) / STAGE_BYTES;
   static constexpr int EPI_BYTES = 4 * 2 * 4096;  // per epilogue warp: two 32x32 fp32 staging tiles
-  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  static constexpr int ACC_COLS = 2 * BN;
+  static constexpr int NEED_COLS = ACC_COLS + (A_TS ? STAGES * 64 : 0);
+  static constexpr int TMEM_COLS = NEED_COLS <= 32 ? 32 : NEED_COLS <= 64 ? 64 : NEED_COLS <= 128 ? 128 : NEED_COLS <= 256 ? 256 : 512;
+  static_assert(NEED_COLS <= 512, "TMEM overflow");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -49,7 +58,8 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, TcArgs p) {
-  using Cfg = TcCfg<BN>;
+  constexpr bool A_TS = !A_MN;
+  using Cfg = TcCfg<BN, A_TS>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -108,7 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int mb = 0; mb < TBM / 32; ++mb)
               tma_load_2d(sp + mb * 4096, &tmA, &full[s], mt * TBM + mb * 32, kb * TBK);
           }
-          uint8_t* bp = sp + 2 * Cfg::A_BYTES;
+          uint8_t* bp = sp + Cfg::A_SMEM;
           if (!B_MN) {
             tma_load_2d(bp, &tmB, &full[s], kb * TBK, nt * BN);
           } else {
@@ -137,19 +147,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t a_hi = smem_u32(stage_ptr(s));
           const uint32_t a_lo = a_hi + Cfg::A_BYTES;
-          const uint32_t b_hi = a_hi + 2 * Cfg::A_BYTES;
+          const uint32_t b_hi = a_hi + Cfg::A_SMEM;
           const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+          const uint32_t ta_hi = tmem_base + Cfg::ACC_COLS + s * 64, ta_lo = ta_hi + 32;  // A_TS only
 #pragma unroll
           for (int j = 0; j < TBK / 8; ++j) {
-            const uint32_t ao = A_MN ? j * 1024 : j * 32;
             const uint32_t bo = B_MN ? j * 1024 : j * 32;
-            const uint64_t dah = A_MN ? smem_desc_mnmajor(a_hi + ao, 4096) : smem_desc_kmajor(a_hi + ao);
-            const uint64_t dal = A_MN ? smem_desc_mnmajor(a_lo + ao, 4096) : smem_desc_kmajor(a_lo + ao);
             const uint64_t dbh = B_MN ? smem_desc_mnmajor(b_hi + bo, 4096) : smem_desc_kmajor(b_hi + bo);
             const uint64_t dbl = B_MN ? smem_desc_mnmajor(b_lo + bo, 4096) : smem_desc_kmajor(b_lo + bo);
-            mma_tf32(tacc, dal, dbh, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
-            mma_tf32(tacc, dah, dbl, idesc, 1u);
-            mma_tf32(tacc, dah, dbh, idesc, 1u);
+            const uint32_t acc0 = (kb > kb0 || j > 0) ? 1u : 0u;
+            if (A_TS) {
+              mma_tf32_ts(tacc, ta_lo + j * 8, dbh, idesc, acc0);
+              mma_tf32_ts(tacc, ta_hi + j * 8, dbl, idesc, 1u);
+              mma_tf32_ts(tacc, ta_hi + j * 8, dbh, idesc, 1u);
+            } else {
+              const uint32_t ao = j * 1024;
+              const uint64_t dah = smem_desc_mnmajor(a_hi + ao, 4096), dal = smem_desc_mnmajor(a_lo + ao, 4096);
+              mma_tf32(tacc, dal, dbh, idesc, acc0);
+              mma_tf32(tacc, dah, dbl, idesc, 1u);
+              mma_tf32(tacc, dah, dbh, idesc, 1u);
+            }
           }
           mma_commit(&empty[s]);
         }
@@ -168,13 +185,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&full[s], (it / S) & 1);
         uint8_t* sp = stage_ptr(s);
         const float4* a_hi = reinterpret_cast<const float4*>(sp);
-        float4* a_lo = reinterpret_cast<float4*>(sp + Cfg::A_BYTES);
-        const float4* b_hi = reinterpret_cast<const float4*>(sp + 2 * Cfg::A_BYTES);
-        float4* b_lo = reinterpret_cast<float4*>(sp + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+        const float4* b_hi = reinterpret_cast<const float4*>(sp + Cfg::A_SMEM);
+        float4* b_lo = reinterpret_cast<float4*>(sp + Cfg::A_SMEM + Cfg::B_BYTES);
+        if (A_TS) {
+          // this thread owns A row r (== TMEM lane): un-swizzle its 128 B, write hi and lo to TMEM
+          const int r = (warp & 3) * 32 + lane;
+          float hi[32], lo[32];
 #pragma unroll
-        for (int i = 0; i < Cfg::A_BYTES / 16 / 128; ++i) {
-          float4 v = a_hi[tix + i * 128];
-          a_lo[tix + i * 128] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(sp + r * 128 + ((c ^ (r & 7)) << 4));
+            hi[4 * c] = v.x; hi[4 * c + 1] = v.y; hi[4 * c + 2] = v.z; hi[4 * c + 3] = v.w;
+          }
+#pragma unroll
+          for (int q = 0; q < 32; ++q) lo[q] = tf32_residual(hi[q]);
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::ACC_COLS + s * 64;
+          tmem_st32(ta, hi);
+          tmem_st32(ta + 32, lo);
+          tmem_st_wait();
+        } else {
+          float4* a_lo = reinterpret_cast<float4*>(sp + Cfg::A_BYTES);
+#pragma unroll
+          for (int i = 0; i < Cfg::A_BYTES / 16 / 128; ++i) {
+            float4 v = a_hi[tix + i * 128];
+            a_lo[tix + i * 128] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
+          }
         }
 #pragma unroll
         for (int i = 0; i < Cfg::B_BYTES / 16 / 128; ++i) {
@@ -182,6 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           b_lo[tix + i * 128] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
         }
         fence_proxy_async_smem();
+        tc_fence_before();
         mbar_arrive(&ready[s]);
       }
     }
@@ -307,7 +342,7 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t r
 template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcArgs& args, int grid,
                      cudaStream_t stream) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, !A_MN>;
   static bool configured = false;
   if (!configured) {
     SUG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
