@@ -633,3 +633,36 @@ def test_graphed_step_matches_eager(S):
     pe, pg = dict(net_e.named_parameters()), dict(net_g.named_parameters())
     for k in ("g.conv1.conv.0.weight", "g.conv5.weight", "c1.mlp3.weight", "attention_s.bn.weight"):
         assert relerr(pg[k], pe[k]) < 1e-2, k
+
+
+def test_lidar_scale_inference(S):
+    """BASELINE configs[4]: DGCNN inference at LiDAR scale.  N = 4096 against the CPU oracle (teacher
+    forced), N = 16384 through properties only (the reference needs four 1.07 GB N x N tensors per
+    cloud there; the tiled kNN never forms them)."""
+    cls = _load(S.model_pointnet.DGCNN(), "DGCNN_cls", 667).eval()
+    x, _ = O.synth_clouds(1, 4096, 77)
+    ref, trace = oracle_trace(lambda: O.dgcnn_cls(x, O.synth_state("DGCNN_cls", 667), False))
+    with torch.no_grad(), teacher_forced(S, trace):
+        lg = cls(x.to(DEV))
+    assert_close(lg, ref, 1e-3, "DGCNN_cls logits at N=4096")
+    n_diff, wd, wn = knn_report(x.squeeze(-1), S.ops.knn_cm(x.squeeze(-1).to(DEV), 20), 20)
+    print(f"kNN N=4096: {n_diff} rows differ, gap {wn:.1e}")
+    assert wn < 1e-6
+    torch.cuda.reset_peak_memory_stats()
+    xb, _ = O.synth_clouds(1, 16384, 78)
+    xg = xb.to(DEV)
+    with torch.no_grad():
+        out = cls(xg)
+    assert out.shape == (1, 10) and bool(torch.isfinite(out).all())
+    peak = torch.cuda.max_memory_allocated() / 2 ** 20
+    print(f"N=16384 inference peak memory {peak:.0f} MiB (one N x N fp32 matrix alone would be 1024 MiB)")
+    assert peak < 900
+    idx = S.ops.knn_cm(xg.squeeze(-1), 20).long()
+    assert bool((idx[..., 0] == torch.arange(16384, device=DEV)).all())
+    # exactness on a slice of rows: brute force on the GPU for 256 query rows
+    q = xg.squeeze(-1)[0].t()[:256]                     # [256,3]
+    allp = xg.squeeze(-1)[0].t()                        # [N,3]
+    D = -((q[:, None, :] - allp[None, :, :]) ** 2).sum(-1)
+    kth = torch.gather(D, 1, idx[0, :256]).min(-1)[0]
+    mask = torch.ones_like(D, dtype=torch.bool).scatter_(1, idx[0, :256], False)
+    assert bool((torch.where(mask, D, torch.full_like(D, -1e30)).max(-1)[0] <= kth + 1e-6).all())
