@@ -47,7 +47,7 @@ int sug_knn_f32(const float* x, int B, int C, int N, int k, int64_t sb, int64_t 
                 int32_t* idx, void* ws, size_t ws_bytes, sug_stream_t stream);
 
 /* Transposed neighbour graph used by the EdgeConv backward: for every point j the list of
- * (i, slot) with idx[i][slot] == j, sorted by (i, slot).  rev_ptr [B, N+1] (offsets local to
+ * (i, slot) with idx[i][slot] == j, in unspecified order.  rev_ptr [B, N+1] (offsets local to
  * the cloud), rev_edge [B, N*k] = (i << 8) | slot.  Requires k <= 255. */
 int sug_knn_reverse(const int32_t* idx, int B, int N, int k, int32_t* rev_ptr, int32_t* rev_edge,
                     sug_stream_t stream);

@@ -170,8 +170,9 @@ int knn_simt(const float* x, int B, int C, int N, int k, long long sb, long long
 }
 
 // ---- transposed graph -------------------------------------------------------------------------
-// One CTA per cloud: counting sort of the N*k edges by destination, then each destination's list
-// is put in (source, slot) order so that the backward's accumulation order is deterministic.
+// One CTA per cloud: counting sort of the N*k edges by destination.  The order inside a destination's
+// list is the arrival order of the atomics (unspecified): sorting the lists would be quadratic in the
+// in-degree, and feature-space kNN graphs have hubs with in-degrees in the thousands.
 __global__ void __launch_bounds__(1024)
 knn_reverse_kernel(const int* __restrict__ idx, int N, int k, int* __restrict__ rev_ptr, int* __restrict__ rev_edge) {
   extern __shared__ int sm[];
@@ -228,20 +229,6 @@ knn_reverse_kernel(const int* __restrict__ idx, int N, int k, int* __restrict__ 
     int pos = atomicAdd(&deg[j], 1);
     int i = e / k, s = e - i * k;
     eb[ptr[j] + pos] = (i << 8) | s;
-  }
-  __syncthreads();
-  // deterministic order: insertion sort of every destination's list (mean length k)
-  for (int j = tid; j < N; j += nt) {
-    int lo = ptr[j], hi = ptr[j + 1];
-    for (int a = lo + 1; a < hi; ++a) {
-      int v = eb[a];
-      int p = a - 1;
-      while (p >= lo && eb[p] > v) {
-        eb[p + 1] = eb[p];
-        --p;
-      }
-      eb[p + 1] = v;
-    }
   }
 }
 
