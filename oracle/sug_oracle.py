@@ -127,10 +127,11 @@ def farthest_point_sample(xyz: torch.Tensor, npoint: int, start: Optional[torch.
     """point_utils.py:5-26.  xyz [B,3,N] -> int64 [B,npoint].  The random start index is
     drawn with torch.randint on the CPU generator exactly like line 17 unless given."""
     B, _, N = xyz.shape
-    cent = torch.zeros(B, npoint, dtype=torch.long)
-    dist = torch.ones(B, N) * 1e10
-    far = torch.randint(0, N, (B,), dtype=torch.long) if start is None else start.clone()
-    ar = torch.arange(B)
+    dev = xyz.device
+    cent = torch.zeros(B, npoint, dtype=torch.long, device=dev)
+    dist = torch.ones(B, N, device=dev) * 1e10
+    far = (torch.randint(0, N, (B,), dtype=torch.long) if start is None else start.clone()).to(dev)
+    ar = torch.arange(B, device=dev)
     for i in range(npoint):
         cent[:, i] = far
         c = xyz[ar, :, far].view(B, 3, 1)
@@ -144,7 +145,7 @@ def index_points(points: torch.Tensor, idx: torch.Tensor):
     """point_utils.py:60-83.  points [B,C,N], idx [B,S] or [B,S,K] -> [B,C,S] / [B,C,S,K]."""
     B, C, _ = points.shape
     pt = points.permute(0, 2, 1)
-    out = pt[torch.arange(B).view(B, *([1] * (idx.dim() - 1))), idx]
+    out = pt[torch.arange(B, device=points.device).view(B, *([1] * (idx.dim() - 1))), idx]
     return out.permute(0, 2, 1) if idx.dim() == 2 else out.permute(0, 3, 1, 2)
 
 
@@ -167,7 +168,7 @@ def query_ball_point(radius, nsample, xyz, new_xyz):
     sq = square_distance(new_xyz, xyz)
     if radius is None:
         return torch.sort(sq, dim=-1)[1][:, :, :nsample]
-    g = torch.arange(N).view(1, 1, N).repeat(B, S, 1)
+    g = torch.arange(N, device=xyz.device).view(1, 1, N).repeat(B, S, 1)
     g[sq > radius ** 2] = N
     g = g.sort(dim=-1)[0][:, :, :nsample]
     first = g[:, :, :1].expand(-1, -1, nsample)
@@ -241,7 +242,7 @@ def transform_net(x, sd: State, p: str, training: bool, K: int):
     y = fc_layer(y, sd, p + ".fc1", "leakyrelu")
     y = fc_layer(y, sd, p + ".fc2", "leakyrelu")
     y = F.linear(y, sd[p + ".fc3.weight"], sd[p + ".fc3.bias"])
-    return (y + torch.eye(K).view(1, K * K)).view(-1, K, K)
+    return (y + torch.eye(K, device=y.device).view(1, K * K)).view(-1, K, K)
 
 
 def pointnet_g(x, sd: State, p: str, training: bool, fps_start=None):
@@ -315,8 +316,8 @@ def dgcnn_cls(x, sd: State, training: bool, drop_p: float = 0.4):
 # --------------------------------------------------------------------------------------
 def one_hot(labels, num_class=10):
     """common_utils.py:161-164."""
-    o = torch.zeros(labels.shape[0], num_class)
-    o[torch.arange(labels.shape[0]), labels] = 1
+    o = torch.zeros(labels.shape[0], num_class, device=labels.device)
+    o[torch.arange(labels.shape[0], device=labels.device), labels] = 1
     return o
 
 
@@ -341,7 +342,7 @@ def mmd2(Kxx, Kxy, Kyy, biased=True, sample_weights=None):
     kyy = (Kyy.sum(dim=1) - dy).sum()
     kxy0 = Kxy.sum(dim=0)
     if sample_weights is not None:
-        kxy0 = sample_weights.reshape(-1) * kxy0
+        kxy0 = sample_weights.reshape(-1).to(kxy0.device) * kxy0  # mmd.py:295 (.to(device='cuda'))
     kxy = kxy0.sum()
     if biased:
         return (kxx + dx.sum()) / (m * m) + (kyy + dy.sum()) / (m * m) - 2.0 * kxy / (m * m)
@@ -429,6 +430,7 @@ class FocalLoss:
         self.gamma = gamma
 
     def __call__(self, preds, labels):
+        self.alpha = self.alpha.to(preds.device)
         ls = F.log_softmax(preds.view(-1, preds.size(-1)), dim=1)
         pt = torch.exp(ls).gather(1, labels.view(-1, 1))
         lg = ls.gather(1, labels.view(-1, 1))
