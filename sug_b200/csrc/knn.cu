@@ -235,15 +235,15 @@ knn_reverse_kernel(const int* __restrict__ idx, int N, int k, int* __restrict__ 
 }  // namespace sug
 
 namespace sug {
-bool knn_tc_supported(int C, int k, long long sn, long long sc, const float* x);
-size_t knn_tc_ws_bytes(int B, int N);
+bool knn_tc_supported(int C, int k, int N, long long sn, long long sc, const float* x);
+size_t knn_tc_ws_bytes(int B, int C, int N);
 int knn_tc(const float* x, int B, int C, int N, int k, long long ld, int* idx, void* ws, size_t ws_bytes,
            cudaStream_t stream);
 }  // namespace sug
 
 extern "C" size_t sug_knn_ws_bytes(int B, int C, int N, int k) {
-  (void)C; (void)k;
-  return sug::knn_tc_ws_bytes(B, N);
+  (void)k;
+  return sug::knn_tc_ws_bytes(B, C, N);
 }
 
 extern "C" int sug_knn_f32(const float* x, int B, int C, int N, int k, int64_t sb, int64_t sn, int64_t sc,
@@ -252,7 +252,7 @@ extern "C" int sug_knn_f32(const float* x, int B, int C, int N, int k, int64_t s
   SUG_CHECK_ARG(B > 0 && C > 0 && N > 0, "knn: bad shape B=%d C=%d N=%d", B, C, N);
   SUG_CHECK_ARG(k > 0 && k <= N && k <= 128, "knn: k=%d must satisfy 1 <= k <= min(N=%d, 128)", k, N);
   // feature inputs: tcgen05 distance tiles; xyz (C = 3) and odd layouts: CUDA cores
-  if (sb == (int64_t)N * sn && sug::knn_tc_supported(C, k, sn, sc, x))
+  if (sb == (int64_t)N * sn && sug::knn_tc_supported(C, k, N, sn, sc, x))
     return sug::knn_tc(x, B, C, N, k, sn, idx, ws, ws_bytes, (cudaStream_t)stream);
   return sug::knn_simt(x, B, C, N, k, sb, sn, sc, idx, (cudaStream_t)stream);
 }
