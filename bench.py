@@ -228,9 +228,17 @@ def _main(args, rank, emit):
     trace("eager warm-up")
     for i in range(args.warmup):
         run_step(*dev_batches[i % len(dev_batches)])
-    _lib.prof_reset(mask=0xFFFFFFFF)
-    run_step(*dev_batches[0])
-    prof1 = _lib.prof_collect()
+    prof1 = None
+    for i in range(2):  # two instrumented steps, per-class minimum: one-off stalls must not pick the class
+        _lib.prof_reset(mask=0xFFFFFFFF)
+        run_step(*dev_batches[i % len(dev_batches)])
+        pr = _lib.prof_collect()
+        if prof1 is None:
+            prof1 = pr
+        else:
+            for k, v in pr.items():
+                if v["launches"] and v["ms"] < prof1[k]["ms"]:
+                    prof1[k] = v
     dom = max(prof1.items(), key=lambda kv: kv[1]["ms"])[0]
     breakdown = {k: round(v["ms"], 4) for k, v in prof1.items() if v["launches"]}
 

@@ -62,7 +62,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = TcCfg<BN, A_TS>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment as an OFFSET from the __shared__ symbol: the pointer stays in the shared address space (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* epi_smem = smem + S * Cfg::STAGE_BYTES;  // 1024 B aligned (stage sizes are multiples of 1024)
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* full = bars;            // [S]  TMA -> split

@@ -1,19 +1,29 @@
 // Fused pairwise distance + top-k on the tensor cores (reference: model/model_utils.py:178-185).
 //
-// For feature inputs (C >= 16) the -2 X X^T term is a dense contraction.  A small pre-pass writes the
-// squared norms and the tf32 residuals lo(X) = X - hi(X) once per call; the main kernel is persistent:
-// each CTA owns blocks of 128 query points of one cloud and streams that cloud's candidates in tiles
-// of 128.  Every (query block, candidate tile, 32-channel slab) is one TMA stage {A_hi, A_lo, B_hi,
-// B_lo} (SWIZZLE_128B) consumed by 3 x 4 tcgen05.mma.kind::tf32 (fp32-accurate hi/lo split, see
-// gemm_tc.cu) into a double-buffered TMEM accumulator.  Selection is the expensive part (a sorted
-// register list per query row, ~100 instructions per accepted candidate, latency bound), so BOTH
-// remaining warp groups do it: group g takes the tiles that land in TMEM buffer g, keeps its own
-// top-k per row straight out of tcgen05.ld, and the two lists are merged at the end of the query
-// block.  Two CTAs share an SM (16 selection warps).  The N x N matrix exists only tile by tile in
-// TMEM.  Key = (-|x_i|^2 + 2 x_i.x_j) - |x_j|^2, the reference's operation order.
+// For feature inputs (16 <= C <= 128, k = 20 or 40) the -2 X X^T term is a dense contraction.  A persistent
+// CTA per SM owns blocks of 128 query points of one cloud.  The block's query slabs are loaded ONCE
+// (TMA), split into tf32 hi / lo parts and parked in TMEM (tcgen05.st) for the whole block; the
+// cloud's candidates then stream through a 3-stage TMA ring in tiles of 128 (only the raw candidate
+// slab crosses L2 -> shared memory; its lo part is produced next to it), and every (tile, 32-channel
+// slab) is consumed by 3 x 4 tcgen05.mma.kind::tf32 with the A operand read from TMEM (fp32-accurate
+// hi/lo split, see gemm_tc.cu) into a double-buffered TMEM accumulator.  The N x N matrix exists only
+// tile by tile in TMEM.
+//
+// Selection is what bounds this kernel (ALU pipe: a streaming sorted-list insert costs ~100 min/max/
+// select per accepted candidate and ~5 k log-many candidates are accepted per row), so the candidates
+// are swept TWICE -- the tensor pipe is nearly idle, recomputing the tile is free:
+//   sweep 0: every thread keeps 32 running maxima (candidate j -> slot j mod 32), sorts them with a
+//            32-input odd-even merge network and the k-th largest over the row's 64 slot maxima (two
+//            threads per row, see below) is a lower bound T <= (k-th largest key);
+//   sweep 1: candidates with key >= T (about k + a few per row) are appended to a per-row list in
+//            shared memory with predicated stores -- no data-dependent loop, no divergence;
+//   final:   rank of every listed candidate by counting, out[rank] = id for rank < k (sorted output).
+// Two selection groups (4 warps each) alternate over the accumulator buffers, so a query row is served
+// by two threads (one per group) which exchange T, list sizes and lists through shared memory.
+// Key = (-|x_i|^2 + 2 x_i.x_j) - |x_j|^2, the reference's operation order.
+#include <cfloat>
 #include <type_traits>
 
-#include "knn_select.cuh"
 #include "tc_common.cuh"
 
 namespace sug {
@@ -22,12 +32,12 @@ using namespace tc;
 
 constexpr int QBN = 128;                       // candidates per tile (UMMA N)
 constexpr int QTILE_BYTES = 128 * 32 * 4;      // one [128 x 32] fp32 operand block
-constexpr int QSTAGE_BYTES = 4 * QTILE_BYTES;  // A hi/lo + B hi/lo
-constexpr int QTHREADS = 320;
+constexpr int QSTAGE_BYTES = 2 * QTILE_BYTES;  // B hi + B lo
+constexpr int QMAXKB = 4;                      // C <= 128
+constexpr int QTHREADS = 448;                  // TMA, MMA, 4 split warps, 2 x 4 selection warps
 
-// xx[row] = |x_row|^2 ; lo[row][c] = x - (x with the low 13 mantissa bits cleared)
-__global__ void knn_prep_kernel(const float* __restrict__ x, long long ld, long long P, int C, float* __restrict__ xx,
-                                float* __restrict__ lo) {
+// xx[row] = |x_row|^2
+__global__ void knn_prep_kernel(const float* __restrict__ x, long long ld, long long P, int C, float* __restrict__ xx) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= P) return;
@@ -36,7 +46,6 @@ __global__ void knn_prep_kernel(const float* __restrict__ x, long long ld, long 
   for (int c = lane; c < C; c += 32) {
     const float v = __ldg(xr + c);
     s = fmaf(v, v, s);
-    lo[row * C + c] = tf32_residual(v);
   }
   s = warp_sum(s);
   if (lane == 0) xx[row] = s;
@@ -49,42 +58,130 @@ struct KnnTcArgs {
   int mtiles_per_cloud, ntiles;
 };
 
-// K > 0: compile-time k (register-resident sorted lists, two selection groups);
-// K == 0: any k (heap in shared memory, one selection group).
+// ---- 32-input odd-even merge sort (Batcher), descending, on registers: 191 compare-exchanges ----
+__device__ __forceinline__ void cex(float& a, float& b) {
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  a = hi;
+  b = lo;
+}
+template <int LO, int N, int R>
+__device__ __forceinline__ void oe_merge(float (&a)[32]) {
+  constexpr int M = R * 2;
+  if constexpr (M < N) {
+    oe_merge<LO, N, M>(a);
+    oe_merge<LO + R, N, M>(a);
+#pragma unroll
+    for (int i = LO + R; i + R < LO + N; i += M) cex(a[i], a[i + R]);
+  } else {
+    cex(a[LO], a[LO + R]);
+  }
+}
+template <int LO, int N>
+__device__ __forceinline__ void oe_sort(float (&a)[32]) {
+  if constexpr (N > 1) {
+    oe_sort<LO, N / 2>(a);
+    oe_sort<LO + N / 2, N / 2>(a);
+    oe_merge<LO, N, 1>(a);
+  }
+}
+
+// Shared-memory plan of knn_tc_kernel<K> (offsets from the 1 KB aligned base).
 template <int K>
-__global__ void __launch_bounds__(QTHREADS, (K == 20 ? 2 : 1))
-knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmL, KnnTcArgs p) {
-  constexpr int NG = K > 0 ? 2 : 1;
+struct KnnSmem {
+  static constexpr int CAP = K <= 20 ? 56 : 80;  // list capacity per (row, group): k + 16 (one half chunk) + slack
+  static constexpr int S = K <= 20 ? 4 : 3;      // candidate ring stages
+  static constexpr size_t ring = (size_t)S * QSTAGE_BYTES;
+  static constexpr size_t bars = ring;                       // 256 B
+  static constexpr size_t xxs = bars + 256;                  // [2 buffers][2 groups][128] f32 candidate norms
+  static constexpr size_t tbuf = xxs + 4 * QBN * 4;          // [128] f32 thresholds
+  static constexpr size_t cnts = tbuf + 128 * 4;             // [2][128] i32 list sizes
+  static constexpr size_t vals = cnts + 2 * 128 * 4;         // [2][CAP][128] f32
+  static constexpr size_t ids = vals + 2 * (size_t)CAP * 128 * 4;  // [2][CAP][128] u16
+  static constexpr size_t total = ids + 2 * (size_t)CAP * 128 * 2 + 1024;
+};
+
+// Rare path: a (row, group) list is close to full.  Keep its k best (value desc, position asc),
+// compact, and raise the group's threshold to the k-th kept value.
+template <int K, int CAP>
+__device__ __noinline__ void knn_prune(float* mv, unsigned short* mi, int r, int& cnt, float& T) {
+  uint32_t keep0 = 0, keep1 = 0, keep2 = 0;
+  float newT = INFINITY;
+  for (int i = 0; i < cnt; ++i) {
+    const float vi = mv[i * 128 + r];
+    int rank = 0;
+    for (int j = 0; j < cnt; ++j) {
+      const float vj = mv[j * 128 + r];
+      rank += (vj > vi || (vj == vi && j < i)) ? 1 : 0;
+    }
+    if (rank < K) {
+      if (i < 32) keep0 |= 1u << i;
+      else if (i < 64) keep1 |= 1u << (i - 32);
+      else keep2 |= 1u << (i - 64);
+      newT = fminf(newT, vi);
+    }
+  }
+  int w = 0;
+  for (int i = 0; i < cnt; ++i) {
+    const uint32_t m = i < 32 ? keep0 : (i < 64 ? keep1 : keep2);
+    if ((m >> (i & 31)) & 1u) {
+      mv[w * 128 + r] = mv[i * 128 + r];
+      mi[w * 128 + r] = mi[i * 128 + r];
+      ++w;
+    }
+  }
+  cnt = w;
+  T = fmaxf(T, newT);
+}
+
+template <int K>
+__global__ void __launch_bounds__(QTHREADS, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
+  using L = KnnSmem<K>;
+  constexpr int CAP = L::CAP;
+  constexpr int S = L::S;
+  static_assert(CAP <= 96, "knn_prune keeps three 32-bit masks");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + QSTAGE_BYTES);
-  uint64_t* full = bars;        // TMA -> MMA
-  uint64_t* empty = bars + 1;   // MMA -> TMA
-  uint64_t* tfull = bars + 2;   // [2] MMA -> selection
-  uint64_t* tempty = bars + 4;  // [2] selection -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  float* xxs = reinterpret_cast<float*>(smem + QSTAGE_BYTES + 256);  // [2 groups][128] candidate norms
-  float* sel = xxs + 2 * QBN;  // group g: stash [32][128] at sel + g*32*128 (K>0) | heap+stash (K==0)
-  // merge buffer: K == 20 aliases group 1's stash (20 value rows + 10 rows of packed 16-bit ids);
-  // K == 40 has its own region behind the two stashes
-  float* mrg = (K == 20) ? (sel + 32 * KTM) : (sel + 2 * 32 * KTM);
+  // 1 KB alignment as an OFFSET from the __shared__ symbol: the pointer stays in the shared address space (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_stage = smem;  // the query slabs borrow the (drained) candidate ring at the start of a block
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  uint64_t* full = bars;             // [S] TMA -> split
+  uint64_t* ready = bars + S;        // [S] split -> MMA
+  uint64_t* empty = bars + 2 * S;    // [S] MMA -> TMA
+  uint64_t* tfull = bars + 3 * S;    // [2] MMA -> selection
+  uint64_t* tempty = bars + 3 * S + 2;  // [2] selection -> MMA
+  uint64_t* a_full = bars + 3 * S + 4;  // TMA(A) -> split
+  uint64_t* a_ready = bars + 3 * S + 5; // split -> MMA, TMA   (A hi/lo are in TMEM, staging is free)
+  uint64_t* a_free = bars + 3 * S + 6;  // MMA -> TMA          (all MMAs of the query block retired)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 7);
+  float* xxs = reinterpret_cast<float*>(smem + L::xxs);
+  float* tbuf = reinterpret_cast<float*>(smem + L::tbuf);
+  int* cnts = reinterpret_cast<int*>(smem + L::cnts);
+  float* vals = reinterpret_cast<float*>(smem + L::vals);
+  unsigned short* ids = reinterpret_cast<unsigned short*>(smem + L::ids);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_m = p.B * p.mtiles_per_cloud;
   const int kbs = (p.C + 31) / 32;
+  constexpr uint32_t A_COL = 2 * QBN;  // TMEM: [0,256) two accumulators, then 64 columns (hi|lo) per slab
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmL);
-    mbar_init(full, 1);
-    mbar_init(empty, 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], 128);
+      mbar_init(&empty[s], 1);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], 128);
     }
+    mbar_init(a_full, 1);
+    mbar_init(a_ready, 128);
+    mbar_init(a_free, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -93,19 +190,22 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x) {
+      uint32_t it = 0, mi = 0;
+      for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x, ++mi) {
         const int b = mt / p.mtiles_per_cloud, r0 = (mt % p.mtiles_per_cloud) * 128;
-        const int grow = b * p.N + r0;
-        for (int nt = 0; nt < p.ntiles; ++nt) {
-          const int gcol = b * p.N + nt * QBN;
-          for (int kb = 0; kb < kbs; ++kb, ++it) {
-            mbar_wait(empty, (it & 1) ^ 1);
-            mbar_arrive_expect_tx(full, QSTAGE_BYTES);
-            tma_load_2d(smem, &tmX, full, kb * 32, grow);
-            tma_load_2d(smem + QTILE_BYTES, &tmL, full, kb * 32, grow);
-            tma_load_2d(smem + 2 * QTILE_BYTES, &tmX, full, kb * 32, gcol);
-            tma_load_2d(smem + 3 * QTILE_BYTES, &tmL, full, kb * 32, gcol);
+        mbar_wait(a_free, (mi & 1) ^ 1);  // previous query block fully consumed: the ring is drained
+        mbar_arrive_expect_tx(a_full, kbs * QTILE_BYTES);
+        for (int kb = 0; kb < kbs; ++kb) tma_load_2d(a_stage + kb * QTILE_BYTES, &tmX, a_full, kb * 32, b * p.N + r0);
+        mbar_wait(a_ready, mi & 1);  // queries are in TMEM: the ring is free for candidates
+        for (int sweep = 0; sweep < 2; ++sweep) {
+          for (int nt = 0; nt < p.ntiles; ++nt) {
+            const int gcol = b * p.N + nt * QBN;
+            for (int kb = 0; kb < kbs; ++kb, ++it) {
+              const int s = it % S;
+              mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+              mbar_arrive_expect_tx(&full[s], QTILE_BYTES);
+              tma_load_2d(smem + (size_t)s * QSTAGE_BYTES, &tmX, &full[s], kb * 32, gcol);
+            }
           }
         }
       }
@@ -114,120 +214,271 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // ===================================== MMA issuer =========================================
     if (lane == 0) {
       constexpr uint32_t idesc = idesc_tf32(128, QBN, 0, 0);
-      uint32_t it = 0, tile_it = 0;
-      const uint32_t a_hi = smem_u32(smem);
-      const uint32_t a_lo = a_hi + QTILE_BYTES, b_hi = a_hi + 2 * QTILE_BYTES, b_lo = a_hi + 3 * QTILE_BYTES;
-      for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x) {
-        for (int nt = 0; nt < p.ntiles; ++nt, ++tile_it) {
+      uint32_t it = 0, tile_it = 0, mi = 0;
+      for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x, ++mi) {
+        mbar_wait(a_ready, mi & 1);
+        tc_fence_after();
+        for (int t = 0; t < 2 * p.ntiles; ++t, ++tile_it) {
           const int ab = tile_it & 1;
           mbar_wait(&tempty[ab], ((tile_it >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tacc = tmem_base + ab * QBN;
           for (int kb = 0; kb < kbs; ++kb, ++it) {
-            mbar_wait(full, it & 1);
+            const int s = it % S;
+            mbar_wait(&ready[s], (it / S) & 1);
             tc_fence_after();
+            const uint32_t b_hi = smem_u32(smem + (size_t)s * QSTAGE_BYTES), b_lo = b_hi + QTILE_BYTES;
+            const uint32_t ta_hi = tmem_base + A_COL + kb * 64, ta_lo = ta_hi + 32;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint64_t dah = smem_desc_kmajor(a_hi + j * 32), dal = smem_desc_kmajor(a_lo + j * 32);
               const uint64_t dbh = smem_desc_kmajor(b_hi + j * 32), dbl = smem_desc_kmajor(b_lo + j * 32);
-              mma_tf32(tacc, dal, dbh, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-              mma_tf32(tacc, dah, dbl, idesc, 1u);
-              mma_tf32(tacc, dah, dbh, idesc, 1u);
+              mma_tf32_ts(tacc, ta_lo + j * 8, dbh, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+              mma_tf32_ts(tacc, ta_hi + j * 8, dbl, idesc, 1u);
+              mma_tf32_ts(tacc, ta_hi + j * 8, dbh, idesc, 1u);
             }
-            mma_commit(empty);
+            mma_commit(&empty[s]);
           }
           mma_commit(&tfull[ab]);
+        }
+        mma_commit(a_free);
+      }
+    }
+  } else if (warp < 6) {
+    // ========================= split: queries -> TMEM (hi, lo), candidates -> lo tile =================
+    const int tix = threadIdx.x - 64;
+    const int r = (warp & 3) * 32 + lane;  // query row == TMEM lane this thread may write
+    uint32_t it = 0, mi = 0;
+    for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x, ++mi) {
+      mbar_wait(a_full, mi & 1);
+      for (int kb = 0; kb < kbs; ++kb) {
+        const uint8_t* sp = a_stage + kb * QTILE_BYTES;
+        float hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(sp + r * 128 + ((c ^ (r & 7)) << 4));
+          hi[4 * c] = v.x; hi[4 * c + 1] = v.y; hi[4 * c + 2] = v.z; hi[4 * c + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) lo[q] = tf32_residual(hi[q]);
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + A_COL + kb * 64;
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+      for (int t = 0; t < 2 * p.ntiles; ++t) {
+        for (int kb = 0; kb < kbs; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(&full[s], (it / S) & 1);
+          const float4* b_hi = reinterpret_cast<const float4*>(smem + (size_t)s * QSTAGE_BYTES);
+          float4* b_lo = reinterpret_cast<float4*>(smem + (size_t)s * QSTAGE_BYTES + QTILE_BYTES);
+#pragma unroll
+          for (int i = 0; i < QTILE_BYTES / 16 / 128; ++i) {
+            const float4 w = b_hi[tix + i * 128];
+            b_lo[tix + i * 128] = make_float4(tf32_residual(w.x), tf32_residual(w.y), tf32_residual(w.z), tf32_residual(w.w));
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&ready[s]);
         }
       }
     }
   } else {
     // ===================================== selection ===========================================
-    const int grp = warp >= 6 ? 0 : 1;  // warps 6-9: group 0, warps 2-5: group 1
-    if (grp < NG) {
-      const int lg = warp & 3;            // TMEM lane quarter this warp may access
-      const int r = lg * 32 + lane;       // query row inside the block == TMEM lane
-      const int gt = (warp - (grp == 0 ? 6 : 2)) * 32 + lane;  // 0..127 inside the group
-      float* gxx = xxs + grp * QBN;
-      typename std::conditional<(K > 0), TopKReg<(K > 0 ? K : 1)>, TopK>::type tk;
-      if constexpr (K > 0) tk.bind(sel + grp * 32 * KTM);
-      else tk.bind(sel, p.k);
-      uint32_t tile_it = 0;
-      for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x) {
-        const int b = mt / p.mtiles_per_cloud, r0 = (mt % p.mtiles_per_cloud) * 128;
-        const int row = r0 + r;
-        const long long cbase = (long long)b * p.N;
-        const float xxq = row < p.N ? __ldg(p.xx + cbase + row) : 0.f;
-        if constexpr (K > 0) tk.init();
-        else tk.init(r);
-        for (int nt = 0; nt < p.ntiles; ++nt, ++tile_it) {
-          const int ab = tile_it & 1;
-          if (NG == 2 && ab != grp) continue;
-          {
-            const int cj = nt * QBN + gt;
-            gxx[gt] = cj < p.N ? __ldg(p.xx + cbase + cj) : 0.f;
-          }
-          if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-          else asm volatile("bar.sync 2, 128;" ::: "memory");
-          mbar_wait(&tfull[ab], (tile_it >> 1) & 1);
-          tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < QBN / 32; ++c) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + ab * QBN + c * 32, v);
-            tmem_ld_wait();
-            const float4* xj = reinterpret_cast<const float4*>(gxx + c * 32);
+    const int grp = warp >= 10 ? 1 : 0;  // warps 6-9: group 0, warps 10-13: group 1
+    const int lg = warp & 3;             // TMEM lane quarter this warp may access
+    const int r = lg * 32 + lane;        // query row inside the block == TMEM lane
+    const int gt = (warp - (grp == 0 ? 6 : 10)) * 32 + lane;  // 0..127 inside the group
+    float* gxx = xxs + grp * QBN;
+    float* mv = vals + (size_t)grp * CAP * 128;            // this thread's list: mv[e * 128 + r]
+    unsigned short* mi = ids + (size_t)grp * CAP * 128;
+    const float* ov = vals + (size_t)(1 - grp) * CAP * 128;  // the row's other list
+    float* xch = vals + (size_t)CAP * 128;                  // group 1's sorted maxima (its list is empty then)
+    uint32_t tile_it = 0;  // accumulator tiles issued before the current query block
+    for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x, tile_it += 2 * p.ntiles) {
+      const int b = mt / p.mtiles_per_cloud, r0 = (mt % p.mtiles_per_cloud) * 128;
+      const int row = r0 + r;
+      const long long cbase = (long long)b * p.N;
+      const float xxq = row < p.N ? __ldg(p.xx + cbase + row) : 0.f;
+      float T = -FLT_MAX;
+      int cnt = 0;
+      float gm[32];
 #pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
-              const float4 n4 = xj[q4];
-              v[4 * q4 + 0] = fmaf(2.f, v[4 * q4 + 0], -xxq) - n4.x;
-              v[4 * q4 + 1] = fmaf(2.f, v[4 * q4 + 1], -xxq) - n4.y;
-              v[4 * q4 + 2] = fmaf(2.f, v[4 * q4 + 2], -xxq) - n4.z;
-              v[4 * q4 + 3] = fmaf(2.f, v[4 * q4 + 3], -xxq) - n4.w;
-            }
-            const int base = nt * QBN + c * 32;
-            const int nvalid = p.N - base;
-            const uint32_t valid = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
-            tk.consider32(r, v, valid, base);
-          }
-          tc_fence_before();
-          mbar_arrive(&tempty[ab]);
-          // the group's norms buffer is rewritten two tiles later, after the group barrier above
-          if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-          else asm volatile("bar.sync 2, 128;" ::: "memory");
-        }
-        if constexpr (K > 0) {
-          // ---- merge the two groups' lists (same rows, disjoint candidate tiles) ----
-          unsigned short* mid = reinterpret_cast<unsigned short*>(mrg + K * KTM);  // [K][128] 16-bit ids
+      for (int q = 0; q < 32; ++q) gm[q] = -INFINITY;
+
+      // tiles t = 0 .. 2*ntiles-1 (sweep 0 then sweep 1); mine are those that land in accumulator `grp`
+      auto load_norm = [&](int t) -> float {
+        const int cj = (t < p.ntiles ? t : t - p.ntiles) * QBN + gt;
+        return (t < 2 * p.ntiles && cj < p.N) ? __ldg(p.xx + cbase + cj) : 0.f;
+      };
+      int t = (int)((tile_it ^ (uint32_t)grp) & 1u);
+      float nx = load_norm(t);
+      int nbuf = 0;
+      bool have_T = false;
+#pragma unroll 1
+      for (;;) {
+        if (!have_T && t >= p.ntiles) {
+          // ---- threshold: k-th largest of the row's 64 slot maxima (each is a real candidate) ----
+          have_T = true;
+          oe_sort<0, 32>(gm);
+          constexpr int NB = K < 32 ? K : 32;
           if (grp == 1) {
 #pragma unroll
-            for (int s = 0; s < K; ++s) {
-              mrg[s * KTM + r] = tk.v[s];
-              mid[s * KTM + r] = (unsigned short)tk.id[s];
-            }
+            for (int s = 0; s < NB; ++s) xch[s * 128 + r] = gm[s];
           }
           asm volatile("bar.sync 3, 256;" ::: "memory");
           if (grp == 0) {
-#pragma unroll 1
-            for (int s = 0; s < K; ++s) {
-              const float key = mrg[s * KTM + r];
-              if (!(key > tk.thr)) break;  // group 1's list is sorted: nothing further can enter
-              tk.insert(key, (int)mid[s * KTM + r]);
-            }
-            if (row < p.N) {
-              int* o = p.idx + (cbase + row) * K;
+            float kth = -INFINITY;  // max over i of min(a[i-1], b[K-i-1]): i values from my maxima, K-i from the other's
 #pragma unroll
-              for (int s = 0; s < K; ++s) o[s] = tk.id[s];
+            for (int i = 0; i <= K; ++i) {
+              const int ia = i - 1, ib = K - i - 1;
+              if (ia >= 32 || ib >= NB) continue;
+              const float av = ia < 0 ? INFINITY : gm[ia];
+              const float bv = ib < 0 ? INFINITY : xch[ib * 128 + r];
+              kth = fmaxf(kth, fminf(av, bv));
             }
+            tbuf[r] = kth;
           }
           asm volatile("bar.sync 4, 256;" ::: "memory");
-        } else {
-          tk.sort_desc(r);
+          T = fmaxf(tbuf[r], -FLT_MAX);
+        }
+        if (t >= 2 * p.ntiles) break;
+        const bool sweep1 = t >= p.ntiles;
+        const int nt = sweep1 ? t - p.ntiles : t;
+        const int ab = grp;
+        const uint32_t my_it = tile_it + (uint32_t)t;
+        float* gx = gxx + nbuf * (2 * QBN);  // double-buffered norms: one group barrier per tile
+        gx[gt] = nx;
+        nx = load_norm(t + 2);  // in flight while this tile is processed
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        mbar_wait(&tfull[ab], (my_it >> 1) & 1);
+        tc_fence_after();
+        const int nh = min(QBN / 16, (p.N - nt * QBN + 15) >> 4);  // 16-candidate half chunks in this tile
+        const uint32_t tsrc = tmem_base + ((uint32_t)(lg * 32) << 16) + ab * QBN;
+
+        // one half chunk: candidates base .. base+15; H = 0/1 -> running-maximum slots 0-15 / 16-31
+        auto process = [&](float (&v)[16], int h, auto Hc) {
+          constexpr int H = decltype(Hc)::value;
+          const int base = nt * QBN + h * 16;
+          const int nvalid = p.N - base;
+          const float4* xj = reinterpret_cast<const float4*>(gx + h * 16);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 n4 = xj[q4];
+            v[4 * q4 + 0] = fmaf(2.f, v[4 * q4 + 0], -xxq) - n4.x;
+            v[4 * q4 + 1] = fmaf(2.f, v[4 * q4 + 1], -xxq) - n4.y;
+            v[4 * q4 + 2] = fmaf(2.f, v[4 * q4 + 2], -xxq) - n4.z;
+            v[4 * q4 + 3] = fmaf(2.f, v[4 * q4 + 3], -xxq) - n4.w;
+          }
+          if (nvalid < 16) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = q < nvalid ? v[q] : -INFINITY;
+          }
+          if (!sweep1) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) gm[H * 16 + q] = fmaxf(gm[H * 16 + q], v[q]);
+          } else {
+            if (cnt > CAP - 16) knn_prune<K, CAP>(mv, mi, r, cnt, T);
+            // branch-free append: every candidate is stored at the list tail, the tail only advances past
+            // accepted ones (mask = -1) -- no predicated in-place pointer updates behind the stores
+            const uint32_t wv0 = smem_u32(mv + r), wi0 = smem_u32(mi + r);
+            uint32_t wv = wv0 + cnt * 512, wi = wi0 + cnt * 256;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              asm volatile(
+                  "{\n"
+                  ".reg .s32 m;\n"
+                  "st.shared.f32 [%0], %2;\n"
+                  "st.shared.u16 [%1], %4;\n"
+                  "set.ge.s32.f32 m, %2, %3;\n"
+                  "mad.lo.s32 %0, m, -512, %0;\n"
+                  "mad.lo.s32 %1, m, -256, %1;\n"
+                  "}\n"
+                  : "+r"(wv), "+r"(wi)
+                  : "f"(v[q]), "f"(T), "h"((unsigned short)(base + q))
+                  : "memory");
+            }
+            cnt = (int)((wv - wv0) >> 9);
+          }
+        };
+
+        // TMEM reads are software-pipelined: the next half chunk is in flight while one is consumed
+        float va[16], vb[16];
+        tmem_ld16(tsrc, va);
+#pragma unroll 1
+        for (int h = 0; h < nh; h += 2) {
+          tmem_ld_wait();
+          if (h + 1 < nh) tmem_ld16(tsrc + (h + 1) * 16, vb);
+          process(va, h, std::integral_constant<int, 0>{});
+          if (h + 1 < nh) {
+            tmem_ld_wait();
+            if (h + 2 < nh) tmem_ld16(tsrc + (h + 2) * 16, va);
+            process(vb, h + 1, std::integral_constant<int, 1>{});
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[ab]);
+        nbuf ^= 1;
+        t += 2;
+      }
+
+      // ---- final: rank by counting over the row's two lists; (value desc, group, position) order ----
+      cnts[grp * 128 + r] = cnt;
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      {
+        const int m_own = cnt, m_oth = cnts[(1 - grp) * 128 + r];
+        int* o = p.idx + (cbase + row) * K;
+#pragma unroll 1
+        for (int i0 = 0; i0 < m_own; i0 += 4) {
+          float vi[4];
+          int rk[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            vi[u] = (i0 + u < m_own) ? mv[(i0 + u) * 128 + r] : INFINITY;
+            rk[u] = 0;
+          }
+          int j = 0;
+#pragma unroll 4
+          for (; j < i0; ++j) {  // earlier positions of my list win ties
+            const float vj = mv[j * 128 + r];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rk[u] += vj >= vi[u] ? 1 : 0;
+          }
+          for (; j < i0 + 4 && j < m_own; ++j) {
+            const float vj = mv[j * 128 + r];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rk[u] += (vj > vi[u] || (vj == vi[u] && j < i0 + u)) ? 1 : 0;
+          }
+#pragma unroll 4
+          for (; j < m_own; ++j) {
+            const float vj = mv[j * 128 + r];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rk[u] += vj > vi[u] ? 1 : 0;
+          }
+          if (grp == 1) {  // group 0's entries win ties
+#pragma unroll 4
+            for (j = 0; j < m_oth; ++j) {
+              const float vj = ov[j * 128 + r];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) rk[u] += vj >= vi[u] ? 1 : 0;
+            }
+          } else {
+#pragma unroll 4
+            for (j = 0; j < m_oth; ++j) {
+              const float vj = ov[j * 128 + r];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) rk[u] += vj > vi[u] ? 1 : 0;
+            }
+          }
           if (row < p.N) {
-            int* o = p.idx + (cbase + row) * p.k;
-            for (int s = 0; s < p.k; ++s) o[s] = tk.hi[s * KTM + r];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (i0 + u < m_own && rk[u] < K) o[rk[u]] = (int)mi[(i0 + u) * 128 + r];
           }
         }
       }
+      asm volatile("bar.sync 4, 256;" ::: "memory");  // lists are reused by the next query block
     }
   }
 
@@ -235,38 +486,32 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
-}
-
-static size_t knn_tc_smem(int k) {
-  size_t sel;
-  if (k == 20) sel = 2 * 32 * KTM;                       // two stashes (the merge aliases the second)
-  else if (k == 40) sel = 2 * 32 * KTM + 40 * KTM * 2;   // + merge values and 16-bit ids (rounded up)
-  else sel = TopK::smem_floats(k);
-  return (size_t)QSTAGE_BYTES + 1024 + 256 + sizeof(float) * (2 * QBN + sel);
 }
 
 template <int K>
-static int knn_tc_launch(const CUtensorMap& tmX, const CUtensorMap& tmL, const KnnTcArgs& a, int grid, size_t smem,
-                         cudaStream_t stream) {
-  static size_t configured = 0;
-  if (smem > configured) {
+static int knn_tc_launch(const CUtensorMap& tmX, const KnnTcArgs& a, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  const size_t smem = KnnSmem<K>::total;
+  if (!configured) {
     SUG_CUDA(cudaFuncSetAttribute(knn_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured = true;
   }
-  knn_tc_kernel<K><<<grid, QTHREADS, smem, stream>>>(tmX, tmL, a);
+  knn_tc_kernel<K><<<grid, QTHREADS, smem, stream>>>(tmX, a);
   SUG_LAUNCH_CHECK();
   return 0;
 }
 
 bool knn_tc_supported(int C, int k, int N, long long sn, long long sc, const float* x) {
-  return C >= 16 && C % 4 == 0 && N < 65536 && sc == 1 && sn % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-         knn_tc_smem(k) <= 227 * 1024;
+  static_assert(KnnSmem<20>::total <= 227 * 1024 && KnnSmem<40>::total <= 227 * 1024, "shared-memory plan");
+  return (k == 20 || k == 40) && C >= 16 && C <= 32 * QMAXKB && C % 4 == 0 && N < 65536 && sc == 1 && sn % 4 == 0 &&
+         (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 }
 
 size_t knn_tc_ws_bytes(int B, int C, int N) {
-  return align_up(sizeof(float) * (size_t)B * N, 256) + align_up(sizeof(float) * (size_t)B * N * C, 256) + 512;
+  (void)C;
+  return align_up(sizeof(float) * (size_t)B * N, 256) + 512;
 }
 
 // x point-major: rows b*N + n with stride ld (sb == N*ld).
@@ -274,27 +519,23 @@ int knn_tc(const float* x, int B, int C, int N, int k, long long ld, int* idx, v
            cudaStream_t stream) {
   Workspace W(ws, ws_bytes);
   float* xx = W.take<float>((size_t)B * N);
-  float* lo = W.take<float>((size_t)B * N * C);
   if (!W.ok()) { set_error("knn: workspace too small (%zu B, need %zu)", ws_bytes, knn_tc_ws_bytes(B, C, N)); return SUG_E_WORKSPACE; }
   const long long P = (long long)B * N;
   {
-    ProfScope ps(KC_MISC, 2.0 * P * C, 4.0 * P * (2.0 * C + 1), stream);
-    knn_prep_kernel<<<cdiv(P * 32, 256), 256, 0, stream>>>(x, ld, P, C, xx, lo);
+    ProfScope ps(KC_MISC, 2.0 * P * C, 4.0 * P * (C + 1), stream);
+    knn_prep_kernel<<<cdiv(P * 32, 256), 256, 0, stream>>>(x, ld, P, C, xx);
   }
   SUG_LAUNCH_CHECK();
-  CUtensorMap tmX, tmL;
+  CUtensorMap tmX;
   SUG_TRY(make_tmap_2d(&tmX, x, (uint64_t)C, (uint64_t)P, (uint64_t)ld, 128));
-  SUG_TRY(make_tmap_2d(&tmL, lo, (uint64_t)C, (uint64_t)P, (uint64_t)C, 128));
   KnnTcArgs a;
   a.xx = xx; a.idx = idx; a.B = B; a.N = N; a.C = C; a.k = k;
   a.mtiles_per_cloud = cdiv(N, 128);
   a.ntiles = cdiv(N, QBN);
-  const size_t smem = knn_tc_smem(k);
-  const int grid = min((k == 20 ? 2 : 1) * num_sms(), B * a.mtiles_per_cloud);
-  ProfScope ps(KC_KNN_TC, 2.0 * B * (double)N * N * C, 4.0 * B * (double)N * (C + k), stream);
-  if (k == 20) return knn_tc_launch<20>(tmX, tmL, a, grid, smem, stream);
-  if (k == 40) return knn_tc_launch<40>(tmX, tmL, a, grid, smem, stream);
-  return knn_tc_launch<0>(tmX, tmL, a, grid, smem, stream);
+  const int grid = min(num_sms(), B * a.mtiles_per_cloud);
+  ProfScope ps(KC_KNN_TC, 2.0 * 2.0 * B * (double)N * N * C, 4.0 * B * (double)N * (C + k), stream);
+  if (k == 20) return knn_tc_launch<20>(tmX, a, grid, stream);
+  return knn_tc_launch<40>(tmX, a, grid, stream);
 }
 
 }  // namespace sug
