@@ -207,6 +207,21 @@ int sug_gemm_tc_f32(const float* a, int64_t lda, int a_mn_major, const float* b,
                     sug_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Optimizer step of the trainer (train_dg_single_gpu.py:191-203, 329-335: three torch.optim.Adam).
+ *   sug_adam_f32: one multi-tensor Adam update (L2 weight decay folded into the gradient, bias
+ *                 corrected, torch's capturable arithmetic).  p/g/m/v_ptrs and sizes are DEVICE arrays
+ *                 with one entry per tensor (addresses as int64); blk_tensor/blk_chunk map every
+ *                 thread block to (tensor, chunk of sug_adam_chunk() elements).  `step` (device
+ *                 float) is incremented first, `lr` is read from device memory, so the call can be
+ *                 captured in a CUDA graph and follows LR schedulers without re-capture.
+ * ------------------------------------------------------------------------------------------- */
+int sug_adam_chunk(void);
+int sug_adam_f32(const int64_t* p_ptrs, const int64_t* g_ptrs, const int64_t* m_ptrs, const int64_t* v_ptrs,
+                 const int64_t* sizes, const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks,
+                 long long n_params, float* step, const float* lr, float beta1, float beta2, float eps,
+                 float weight_decay, sug_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Launch accounting used by bench.py (`gpu_launches`, `roofline`).  Every kernel launch of the
  * library is counted per kernel class together with its algorithmic flops / bytes (formulas in
  * DESIGN.md).  sug_prof_enable(mask) additionally brackets the launches of the selected classes

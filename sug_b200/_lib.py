@@ -49,6 +49,8 @@ SIGNATURES = {
     "sug_linear_bn_act_fwd": (I, [P, L, P, P, P, P, P, P, L, I, I, F, F, F, I, P, P, L, P, P, Z, P]),
     "sug_linear_bn_act_bwd": (I, [P, L, P, L, P, P, P, P, P, L, I, I, F, P, L, P, P, P, P, P, Z, P]),
     "sug_gemm_tc_f32": (I, [P, L, I, P, L, I, P, P, L, I, I, I, P]),
+    "sug_adam_chunk": (I, []),
+    "sug_adam_f32": (I, [P, P, P, P, P, P, P, I, L, P, P, F, F, F, F, P]),
     "sug_prof_num_classes": (I, []),
     "sug_prof_class_name": (c_char_p, [I]),
     "sug_prof_enable": (None, [ctypes.c_uint]),

@@ -45,16 +45,24 @@ def sug_losses(model, data, label, data_t, label_t, criterion, cfg=SUG_CFG, mmd_
             "loss_sem": loss_sem, "pred_s1": pred_s1, "pred_t1": pred_t1}
 
 
-def make_optimizers(model, opt=OPT_CFG, capturable=False):
+def make_optimizers(model, opt=OPT_CFG, capturable=False, fused=None):
     """train_dg_single_gpu.py:191-203: three Adam optimizers; ``g`` is stepped by two of them.
-    ``capturable=True`` keeps Adam's step counters on the device (needed inside a CUDA graph)."""
+    On CUDA the update is ``optim.FusedAdam`` (torch.optim.Adam arithmetic, one multi-tensor launch per
+    param group, graph-capturable by construction); ``fused=False`` selects ``torch.optim.Adam``
+    (``capturable=True`` keeps its step counters on the device for use inside a CUDA graph)."""
     lr, wd = opt["LR"], opt["WEIGHT_DECAY"]
-    kw = dict(weight_decay=wd, capturable=capturable)
+    if fused is None:
+        fused = next(model.parameters()).is_cuda
+    if fused:
+        from .optim import FusedAdam
+        mk = lambda groups, lr_: FusedAdam(groups, lr=lr_, weight_decay=wd)
+    else:
+        mk = lambda groups, lr_: torch.optim.Adam(groups, lr=lr_, weight_decay=wd, capturable=capturable)
     params = [{'params': v} for k, v in model.g.named_parameters() if 'pred_offset' not in k]
-    opt_g = torch.optim.Adam(params, lr=lr, **kw)
-    opt_c = torch.optim.Adam([{'params': model.c1.parameters()}, {'params': model.c2.parameters()}], lr=lr, **kw)
-    opt_dis = torch.optim.Adam([{'params': model.g.parameters()}, {'params': model.attention_s.parameters()},
-                                {'params': model.attention_t.parameters()}], lr=lr * opt["LR_SCALER"], **kw)
+    opt_g = mk(params, lr)
+    opt_c = mk([{'params': model.c1.parameters()}, {'params': model.c2.parameters()}], lr)
+    opt_dis = mk([{'params': model.g.parameters()}, {'params': model.attention_s.parameters()},
+                  {'params': model.attention_t.parameters()}], lr * opt["LR_SCALER"])
     return opt_dis, opt_g, opt_c
 
 
@@ -84,7 +92,7 @@ class GraphedTrainStep:
       * ``focal_loss`` re-gathers its own ``alpha`` on every call (model_utils.py:168); inside the graph
         every step starts from the constructor's alpha, which is identical for the uniform class
         weights used here.
-    ``optimizers`` must be built with ``make_optimizers(..., capturable=True)``.
+    ``optimizers`` come from ``make_optimizers`` (``FusedAdam``; or torch Adam with ``capturable=True``).
     """
 
     def __init__(self, model, optimizers, criterion, batch, points, device, cfg=SUG_CFG, mmd_fn=None,
@@ -200,6 +208,9 @@ class GraphedTrainStep:
         self.data_t.copy_(data_t, non_blocking=True)
         self.label_t.copy_(label_t, non_blocking=True)
         self._draw_fps()
+        for o in self.opts:  # LR schedulers rewrite group['lr'] on the host: refresh the device scalars
+            if hasattr(o, "sync_lr"):
+                o.sync_lr()
         self.graph.replay()
         if self.hook is not None:
             self._tdist.all_reduce(self._flat)

@@ -587,6 +587,35 @@ def test_full_size_properties(S):
     assert int(blk.conv[1].num_batches_tracked) == 2
 
 
+def test_fused_adam_matches_torch(S):
+    """optim.FusedAdam (one multi-tensor launch) against torch.optim.Adam: weight decay, a parameter
+    without gradient, odd sizes, an LR change between steps."""
+    from sug_b200.optim import FusedAdam
+    torch.manual_seed(5)
+    shapes = [(64, 6, 1, 1), (1024,), (513, 7), (3,), (256, 512), (10, 10)]
+    ref = [torch.randn(sh, device=DEV).requires_grad_(True) for sh in shapes]
+    mine = [p.detach().clone().requires_grad_(True) for p in ref]
+    o_ref = torch.optim.Adam([{"params": ref[:3]}, {"params": ref[3:], "lr": 3e-3}], lr=1e-3, weight_decay=5e-4)
+    o_mine = FusedAdam([{"params": mine[:3]}, {"params": mine[3:], "lr": 3e-3}], lr=1e-3, weight_decay=5e-4)
+    for it in range(6):
+        if it == 3:
+            for o in (o_ref, o_mine):
+                o.param_groups[0]["lr"] = 2.5e-4
+        for k, (a, b) in enumerate(zip(ref, mine)):
+            if k == 5:
+                continue  # never receives a gradient: both optimizers must leave it alone
+            g = torch.randn_like(a) * (10.0 ** (k - 2))
+            a.grad, b.grad = g.clone(), g.clone()
+        o_ref.step()
+        o_mine.step()
+        o_ref.zero_grad()
+        o_mine.zero_grad()
+    for k, (a, b) in enumerate(zip(ref, mine)):
+        assert_close(b.detach(), a.detach(), 2e-6, f"fused adam param {k}")
+    assert torch.equal(mine[5].detach(), ref[5].detach())
+    assert float(o_mine.state[mine[0]]["step"]) == 6.0
+
+
 def test_graphed_step_matches_eager(S):
     """The CUDA-graph step (step.GraphedTrainStep) must train exactly like the eager step: same RNG
     consumption for FPS, same losses and weights after a few steps."""
