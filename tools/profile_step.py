@@ -35,3 +35,15 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step.train_step(model, opts, d, l, dt, lt, crit)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+# kernel-only view: library kernels vs PyTorch glue
+from collections import defaultdict
+agg = defaultdict(lambda: [0.0, 0])
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        agg[ev.name][0] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+        agg[ev.name][1] += 1
+ours = sum(v[0] for k, v in agg.items() if "sug::" in k)
+rest = {k: v for k, v in agg.items() if "sug::" not in k}
+print(f"KERNELS: library {ours/1e3:.3f} ms, other {sum(v[0] for v in rest.values())/1e3:.3f} ms")
+for k, v in sorted(rest.items(), key=lambda kv: -kv[1][0])[:40]:
+    print(f"  {v[0]:9.1f} us  x{v[1]:4d}  {k[:150]}")
