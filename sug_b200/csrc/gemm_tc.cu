@@ -102,7 +102,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    // (the whole warp runs the loop; one elected lane issues -- see elect_one_sync)
+    {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % p.tiles_n, mt = (t / p.tiles_n) % p.tiles_m, ks = t / (p.tiles_n * p.tiles_m);
@@ -110,29 +111,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S;
           mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
-          uint8_t* sp = stage_ptr(s);
-          mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES);
-          if (!A_MN) {
-            tma_load_2d(sp, &tmA, &full[s], kb * TBK, mt * TBM);
-          } else {
+          if (elect_one_sync()) {
+            uint8_t* sp = stage_ptr(s);
+            mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+            if (!A_MN) {
+              tma_load_2d(sp, &tmA, &full[s], kb * TBK, mt * TBM);
+            } else {
 #pragma unroll
-            for (int mb = 0; mb < TBM / 32; ++mb)
-              tma_load_2d(sp + mb * 4096, &tmA, &full[s], mt * TBM + mb * 32, kb * TBK);
-          }
-          uint8_t* bp = sp + Cfg::A_SMEM;
-          if (!B_MN) {
-            tma_load_2d(bp, &tmB, &full[s], kb * TBK, nt * BN);
-          } else {
+              for (int mb = 0; mb < TBM / 32; ++mb)
+                tma_load_2d(sp + mb * 4096, &tmA, &full[s], mt * TBM + mb * 32, kb * TBK);
+            }
+            uint8_t* bp = sp + Cfg::A_SMEM;
+            if (!B_MN) {
+              tma_load_2d(bp, &tmB, &full[s], kb * TBK, nt * BN);
+            } else {
 #pragma unroll
-            for (int nb = 0; nb < BN / 32; ++nb)
-              tma_load_2d(bp + nb * 4096, &tmB, &full[s], nt * BN + nb * 32, kb * TBK);
+              for (int nb = 0; nb < BN / 32; ++nb)
+                tma_load_2d(bp + nb * 4096, &tmB, &full[s], nt * BN + nb * 32, kb * TBK);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =========================================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = idesc_tf32(TBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t it = 0, tile_it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
@@ -151,27 +155,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t b_hi = a_hi + Cfg::A_SMEM;
           const uint32_t b_lo = b_hi + Cfg::B_BYTES;
           const uint32_t ta_hi = tmem_base + Cfg::ACC_COLS + s * 64, ta_lo = ta_hi + 32;  // A_TS only
+          // the descriptors of the four 8-wide k-steps differ only in the start-address field
+          // (K-major: +32 B = +2; MN-major: +1024 B = +64)
+          const uint64_t dbh0 = B_MN ? smem_desc_mnmajor(b_hi, 4096) : smem_desc_kmajor(b_hi);
+          const uint64_t dbl0 = B_MN ? smem_desc_mnmajor(b_lo, 4096) : smem_desc_kmajor(b_lo);
+          const uint64_t dah0 = smem_desc_mnmajor(a_hi, 4096), dal0 = smem_desc_mnmajor(a_lo, 4096);  // SS form only
+          constexpr uint64_t bstep = B_MN ? 64 : 2;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int j = 0; j < TBK / 8; ++j) {
-            const uint32_t bo = B_MN ? j * 1024 : j * 32;
-            const uint64_t dbh = B_MN ? smem_desc_mnmajor(b_hi + bo, 4096) : smem_desc_kmajor(b_hi + bo);
-            const uint64_t dbl = B_MN ? smem_desc_mnmajor(b_lo + bo, 4096) : smem_desc_kmajor(b_lo + bo);
-            const uint32_t acc0 = (kb > kb0 || j > 0) ? 1u : 0u;
-            if (A_TS) {
-              mma_tf32_ts(tacc, ta_lo + j * 8, dbh, idesc, acc0);
-              mma_tf32_ts(tacc, ta_hi + j * 8, dbl, idesc, 1u);
-              mma_tf32_ts(tacc, ta_hi + j * 8, dbh, idesc, 1u);
-            } else {
-              const uint32_t ao = j * 1024;
-              const uint64_t dah = smem_desc_mnmajor(a_hi + ao, 4096), dal = smem_desc_mnmajor(a_lo + ao, 4096);
-              mma_tf32(tacc, dal, dbh, idesc, acc0);
-              mma_tf32(tacc, dah, dbl, idesc, 1u);
-              mma_tf32(tacc, dah, dbh, idesc, 1u);
+            for (int j = 0; j < TBK / 8; ++j) {
+              const uint64_t dbh = dbh0 + bstep * j, dbl = dbl0 + bstep * j;
+              const uint32_t acc0 = (kb > kb0 || j > 0) ? 1u : 0u;
+              if (A_TS) {
+                mma_tf32_ts(tacc, ta_lo + j * 8, dbh, idesc, acc0);
+                mma_tf32_ts(tacc, ta_hi + j * 8, dbl, idesc, 1u);
+                mma_tf32_ts(tacc, ta_hi + j * 8, dbh, idesc, 1u);
+              } else {
+                const uint64_t dah = dah0 + 64 * j, dal = dal0 + 64 * j;
+                mma_tf32(tacc, dal, dbh, idesc, acc0);
+                mma_tf32(tacc, dah, dbl, idesc, 1u);
+                mma_tf32(tacc, dah, dbh, idesc, 1u);
+              }
             }
+            mma_commit(&empty[s]);
+            if (kb == kb1 - 1) mma_commit(&tfull[ab]);
           }
-          mma_commit(&empty[s]);
+          __syncwarp();
         }
-        mma_commit(&tfull[ab]);
       }
     }
   } else if (warp < 6) {
@@ -315,7 +325,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows,
-                 bool swizzle32b) {
+                 bool swizzle32b, uint32_t box_inner, int l2promo) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SUG_E_UNSUPPORTED; }
   SUG_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 4 == 0,
@@ -330,11 +340,14 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t r
   }
   cuuint64_t gdim[2] = {inner, rows};
   cuuint64_t gstr[1] = {ld * sizeof(float)};
-  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_inner != 32 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                   : (swizzle32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
+                   l2promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                : (l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SUG_E_BADARG; }
   return 0;

@@ -22,6 +22,7 @@
 // by two threads (one per group) which exchange T, list sizes and lists through shared memory.
 // Key = (-|x_i|^2 + 2 x_i.x_j) - |x_j|^2, the reference's operation order.
 #include <cfloat>
+#include <cstdlib>
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -56,6 +57,7 @@ struct KnnTcArgs {
   int* idx;         // [B,N,k]
   int B, N, C, k;
   int mtiles_per_cloud, ntiles;
+  int dbg;  // development: bit 0 = skip the selection work (times the TMA -> split -> MMA pipeline alone)
 };
 
 // ---- 32-input odd-even merge sort (Batcher), descending, on registers: 191 compare-exchanges ----
@@ -189,13 +191,17 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    // (the whole warp runs the loop; one elected lane issues -- see elect_one_sync)
+    {
       uint32_t it = 0, mi = 0;
       for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x, ++mi) {
         const int b = mt / p.mtiles_per_cloud, r0 = (mt % p.mtiles_per_cloud) * 128;
         mbar_wait(a_free, (mi & 1) ^ 1);  // previous query block fully consumed: the ring is drained
-        mbar_arrive_expect_tx(a_full, kbs * QTILE_BYTES);
-        for (int kb = 0; kb < kbs; ++kb) tma_load_2d(a_stage + kb * QTILE_BYTES, &tmX, a_full, kb * 32, b * p.N + r0);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(a_full, kbs * QTILE_BYTES);
+          for (int kb = 0; kb < kbs; ++kb) tma_load_2d(a_stage + kb * QTILE_BYTES, &tmX, a_full, kb * 32, b * p.N + r0);
+        }
+        __syncwarp();
         mbar_wait(a_ready, mi & 1);  // queries are in TMEM: the ring is free for candidates
         for (int sweep = 0; sweep < 2; ++sweep) {
           for (int nt = 0; nt < p.ntiles; ++nt) {
@@ -203,8 +209,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
             for (int kb = 0; kb < kbs; ++kb, ++it) {
               const int s = it % S;
               mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
-              mbar_arrive_expect_tx(&full[s], QTILE_BYTES);
-              tma_load_2d(smem + (size_t)s * QSTAGE_BYTES, &tmX, &full[s], kb * 32, gcol);
+              if (elect_one_sync()) {
+                mbar_arrive_expect_tx(&full[s], QTILE_BYTES);
+                tma_load_2d(smem + (size_t)s * QSTAGE_BYTES, &tmX, &full[s], kb * 32, gcol);
+              }
+              __syncwarp();
             }
           }
         }
@@ -212,7 +221,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =========================================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = idesc_tf32(128, QBN, 0, 0);
       uint32_t it = 0, tile_it = 0, mi = 0;
       for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x, ++mi) {
@@ -227,20 +236,28 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
             const int s = it % S;
             mbar_wait(&ready[s], (it / S) & 1);
             tc_fence_after();
-            const uint32_t b_hi = smem_u32(smem + (size_t)s * QSTAGE_BYTES), b_lo = b_hi + QTILE_BYTES;
+            const uint32_t b_hi = smem_u32(smem + (size_t)s * QSTAGE_BYTES);
+            // descriptors of the 8-wide k-steps differ only in the start address field (+32 B = +2)
+            const uint64_t dbh0 = smem_desc_kmajor(b_hi), dbl0 = smem_desc_kmajor(b_hi + QTILE_BYTES);
             const uint32_t ta_hi = tmem_base + A_COL + kb * 64, ta_lo = ta_hi + 32;
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint64_t dbh = smem_desc_kmajor(b_hi + j * 32), dbl = smem_desc_kmajor(b_lo + j * 32);
-              mma_tf32_ts(tacc, ta_lo + j * 8, dbh, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-              mma_tf32_ts(tacc, ta_hi + j * 8, dbl, idesc, 1u);
-              mma_tf32_ts(tacc, ta_hi + j * 8, dbh, idesc, 1u);
+              for (int j = 0; j < 4; ++j) {
+                const uint64_t dbh = dbh0 + 2 * j, dbl = dbl0 + 2 * j;
+                mma_tf32_ts(tacc, ta_lo + j * 8, dbh, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                if (!(p.dbg & 4)) {
+                mma_tf32_ts(tacc, ta_hi + j * 8, dbl, idesc, 1u);
+                mma_tf32_ts(tacc, ta_hi + j * 8, dbh, idesc, 1u);
+                }
+              }
+              mma_commit(&empty[s]);
+              if (kb == kbs - 1) mma_commit(&tfull[ab]);
             }
-            mma_commit(&empty[s]);
+            __syncwarp();
           }
-          mma_commit(&tfull[ab]);
         }
-        mma_commit(a_free);
+        if (elect_one_sync()) mma_commit(a_free);
+        __syncwarp();
       }
     }
   } else if (warp < 6) {
@@ -273,10 +290,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
           mbar_wait(&full[s], (it / S) & 1);
           const float4* b_hi = reinterpret_cast<const float4*>(smem + (size_t)s * QSTAGE_BYTES);
           float4* b_lo = reinterpret_cast<float4*>(smem + (size_t)s * QSTAGE_BYTES + QTILE_BYTES);
+          if (!(p.dbg & 2)) {
 #pragma unroll
           for (int i = 0; i < QTILE_BYTES / 16 / 128; ++i) {
             const float4 w = b_hi[tix + i * 128];
             b_lo[tix + i * 128] = make_float4(tf32_residual(w.x), tf32_residual(w.y), tf32_residual(w.z), tf32_residual(w.w));
+          }
           }
           fence_proxy_async_smem();
           mbar_arrive(&ready[s]);
@@ -407,7 +426,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
         float va[16], vb[16];
         tmem_ld16(tsrc, va);
 #pragma unroll 1
-        for (int h = 0; h < nh; h += 2) {
+        for (int h = 0; h < ((p.dbg & 1) ? 0 : nh); h += 2) {
           tmem_ld_wait();
           if (h + 1 < nh) tmem_ld16(tsrc + (h + 1) * 16, vb);
           process(va, h, std::integral_constant<int, 0>{});
@@ -527,11 +546,19 @@ int knn_tc(const float* x, int B, int C, int N, int k, long long ld, int* idx, v
   }
   SUG_LAUNCH_CHECK();
   CUtensorMap tmX;
-  SUG_TRY(make_tmap_2d(&tmX, x, (uint64_t)C, (uint64_t)P, (uint64_t)ld, 128));
+  static const int dbgv = getenv("SUG_KNN_DEBUG") ? atoi(getenv("SUG_KNN_DEBUG")) : 0;
+  if (dbgv & 8) SUG_TRY(make_tmap_2d(&tmX, x, (uint64_t)C, (uint64_t)P, (uint64_t)ld, 64, false, 64));   // timing experiment: 64 rows x 256 B
+  else if (dbgv & 16) SUG_TRY(make_tmap_2d(&tmX, x, (uint64_t)C, (uint64_t)P, (uint64_t)ld, 128, false, 32, 2));  // 256 B L2 promotion
+  else if (dbgv & 32) SUG_TRY(make_tmap_2d(&tmX, x, (uint64_t)C, (uint64_t)P, (uint64_t)ld, 128, false, 32, 0));  // no L2 promotion
+  else SUG_TRY(make_tmap_2d(&tmX, x, (uint64_t)C, (uint64_t)P, (uint64_t)ld, 128));
   KnnTcArgs a;
   a.xx = xx; a.idx = idx; a.B = B; a.N = N; a.C = C; a.k = k;
   a.mtiles_per_cloud = cdiv(N, 128);
   a.ntiles = cdiv(N, QBN);
+  {
+    static const int dbg = getenv("SUG_KNN_DEBUG") ? atoi(getenv("SUG_KNN_DEBUG")) : 0;
+    a.dbg = dbg;
+  }
   const int grid = min(num_sms(), B * a.mtiles_per_cloud);
   ProfScope ps(KC_KNN_TC, 2.0 * 2.0 * B * (double)N * N * C, 4.0 * B * (double)N * (C + k), stream);
   if (k == 20) return knn_tc_launch<20>(tmX, a, grid, stream);

@@ -36,6 +36,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// One lane of a fully converged warp (elect.sync).  Issuing tcgen05.mma / TMA from `if (elect_one_sync())`
+// inside warp-uniform code lets the compiler keep descriptors in uniform registers and emit the
+// instruction once; issuing it from `if (lane == 0)` makes it wrap EVERY such instruction in an
+// elect / R2UR / BRA.U.ANY loop (~12 extra dependent instructions per MMA, measured to cost more than the
+// MMA itself).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // Bounded wait: a pipeline bug traps (error returned to the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -207,6 +223,6 @@ __device__ __forceinline__ float tf32_residual(float x) {
 // swizzle, out-of-bounds elements read as zero.
 // swizzle32b: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (MN-major operands) instead of SWIZZLE_128B.
 int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows,
-                 bool swizzle32b = false);
+                 bool swizzle32b = false, uint32_t box_inner = 32, int l2promo = 1);
 
 }  // namespace sug
