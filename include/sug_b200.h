@@ -184,6 +184,22 @@ int sug_interp_fwd(const float* f, const int32_t* idx, const float* w, int B, in
 int sug_interp_bwd(const float* g, const float* f, const int32_t* idx, const float* w, int B, int N, int S,
                    int K, int C, float* df, float* dw, sug_stream_t stream);
 
+/* Node offsets (model_utils.py:107-117: tanh(pred_offset(group - centre)) * (group_xyz - centre_xyz),
+ * mean over the ball) and the 3-NN inverse-squared-distance interpolation weights
+ * (point_utils.py:141-160), each fused into one kernel with its backward.
+ *   h [B,N,3] = pred_offset weights applied per point (the conv is linear and bias-free),
+ *   xyz [B,3,N], fidx [B,S] centres, gidx [B,S,G] ball members -> out [B,S,3]; dh [B,N,3] zeroed by the caller.
+ *   nodes [B,S,3], idx [B,N,K] (K <= 8) -> w [B,N,K]; dnodes [B,S,3] zeroed by the caller.
+ * The backward kernels scatter with float atomics (summation order not fixed). */
+int sug_node_offset_fwd(const float* h, const float* xyz, const int32_t* fidx, const int32_t* gidx, int B, int N,
+                        int S, int G, float* out, sug_stream_t stream);
+int sug_node_offset_bwd(const float* gout, const float* h, const float* xyz, const int32_t* fidx,
+                        const int32_t* gidx, int B, int N, int S, int G, float* dh, sug_stream_t stream);
+int sug_interp_weight_fwd(const float* xyz, const float* nodes, const int32_t* idx, int B, int N, int S, int K,
+                          float* w, sug_stream_t stream);
+int sug_interp_weight_bwd(const float* gw, const float* xyz, const float* nodes, const int32_t* idx, int B, int N,
+                          int S, int K, float* dnodes, sug_stream_t stream);
+
 /* Plain fp32 GEMM used inside the entry points above, exported for tests:
  * C[M,N] = A * B^T (+ bias[n]) with A(m,k) = a[m*sam + k*sak], B(n,k) = b[n*sbn + k*sbk]. */
 int sug_gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,

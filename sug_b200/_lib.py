@@ -49,6 +49,10 @@ SIGNATURES = {
     "sug_linear_bn_act_fwd": (I, [P, L, P, P, P, P, P, P, L, I, I, F, F, F, I, P, P, L, P, P, Z, P]),
     "sug_linear_bn_act_bwd": (I, [P, L, P, L, P, P, P, P, P, L, I, I, F, P, L, P, P, P, P, P, Z, P]),
     "sug_gemm_tc_f32": (I, [P, L, I, P, L, I, P, P, L, I, I, I, P]),
+    "sug_node_offset_fwd": (I, [P, P, P, P, I, I, I, I, P, P]),
+    "sug_node_offset_bwd": (I, [P, P, P, P, P, I, I, I, I, P, P]),
+    "sug_interp_weight_fwd": (I, [P, P, P, I, I, I, I, P, P]),
+    "sug_interp_weight_bwd": (I, [P, P, P, P, I, I, I, I, P, P]),
     "sug_adam_chunk": (I, []),
     "sug_adam_f32": (I, [P, P, P, P, P, P, P, I, L, P, P, F, F, F, F, P]),
     "sug_prof_num_classes": (I, []),

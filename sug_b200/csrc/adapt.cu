@@ -442,3 +442,171 @@ extern "C" int sug_three_nn(const float* xyz, const float* nodes, int B, int N, 
   SUG_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- node offsets and interpolation weights of the adapt layer, fused -----------------------------------
+// (model_utils.py:107-117 and point_utils.py:134-160; the reference spells these out as ~25 tensor ops
+// with three advanced-index gathers whose backward is a sort-based index_put each.)
+namespace sug {
+
+// node_offset[b,s,:] = mean_j tanh(h[g_j] - h[f]) * (loc[g_j] - loc[f]),  g = group[b,s,:], f = fidx[b,s]
+// xyz is the reference's [B,3,N] layout; h is [B,N,3].
+__global__ void node_offset_fwd_kernel(const float* __restrict__ h, const float* __restrict__ xyz,
+                                       const int* __restrict__ fidx, const int* __restrict__ gidx, int N, int S, int G,
+                                       float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  if (warp >= S) return;
+  const float* hb = h + (size_t)b * N * 3;
+  const float* xb = xyz + (size_t)b * 3 * N;
+  const int f = __ldg(fidx + (size_t)b * S + warp);
+  const float hf[3] = {__ldg(hb + f * 3), __ldg(hb + f * 3 + 1), __ldg(hb + f * 3 + 2)};
+  const float lf[3] = {__ldg(xb + f), __ldg(xb + N + f), __ldg(xb + 2 * N + f)};
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int j = lane; j < G; j += 32) {
+    const int g = __ldg(gidx + ((size_t)b * S + warp) * G + j);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += tanhf(__ldg(hb + g * 3 + c) - hf[c]) * (__ldg(xb + c * N + g) - lf[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) acc[c] = warp_sum(acc[c]);
+  if (lane == 0) {
+    const float inv = 1.f / (float)G;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[((size_t)b * S + warp) * 3 + c] = acc[c] * inv;
+  }
+}
+
+// dh (zeroed) += scatter of d node_offset through tanh'; float atomics (summation order is not fixed)
+__global__ void node_offset_bwd_kernel(const float* __restrict__ go, const float* __restrict__ h,
+                                       const float* __restrict__ xyz, const int* __restrict__ fidx,
+                                       const int* __restrict__ gidx, int N, int S, int G, float* __restrict__ dh) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  if (warp >= S) return;
+  const float* hb = h + (size_t)b * N * 3;
+  const float* xb = xyz + (size_t)b * 3 * N;
+  float* db = dh + (size_t)b * N * 3;
+  const int f = __ldg(fidx + (size_t)b * S + warp);
+  const float inv = 1.f / (float)G;
+  float hf[3], lf[3], g3[3], accf[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    hf[c] = __ldg(hb + f * 3 + c);
+    lf[c] = __ldg(xb + c * N + f);
+    g3[c] = __ldg(go + ((size_t)b * S + warp) * 3 + c) * inv;
+  }
+  for (int j = lane; j < G; j += 32) {
+    const int g = __ldg(gidx + ((size_t)b * S + warp) * G + j);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float t = tanhf(__ldg(hb + g * 3 + c) - hf[c]);
+      const float d = g3[c] * (__ldg(xb + c * N + g) - lf[c]) * (1.f - t * t);
+      atomicAdd(db + g * 3 + c, d);
+      accf[c] += d;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) accf[c] = warp_sum(accf[c]);
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(db + f * 3 + c, -accf[c]);
+  }
+}
+
+// w[b,n,t] = (1/d_t) / sum_u (1/d_u),  d_t = max(|x_n|^2 + |y_t|^2 - 2 x_n.y_t, 1e-10),  y_t = nodes[b, idx[b,n,t]]
+// nodes is [B,S,3]; K <= 8.
+__global__ void interp_weight_fwd_kernel(const float* __restrict__ xyz, const float* __restrict__ nodes,
+                                         const int* __restrict__ idx, int N, int S, int K, float* __restrict__ w) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (n >= N) return;
+  const float* xb = xyz + (size_t)b * 3 * N;
+  const float x[3] = {__ldg(xb + n), __ldg(xb + N + n), __ldg(xb + 2 * N + n)};
+  const float xx = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+  float r[8], R = 0.f;
+  for (int t = 0; t < K; ++t) {
+    const float* y = nodes + ((size_t)b * S + __ldg(idx + ((size_t)b * N + n) * K + t)) * 3;
+    const float y0 = __ldg(y), y1 = __ldg(y + 1), y2 = __ldg(y + 2);
+    const float dot = x[0] * y0 + x[1] * y1 + x[2] * y2;
+    float d = -2.f * dot + xx + (y0 * y0 + y1 * y1 + y2 * y2);
+    d = d < 1e-10f ? 1e-10f : d;
+    r[t] = 1.f / d;
+    R += r[t];
+  }
+  for (int t = 0; t < K; ++t) w[((size_t)b * N + n) * K + t] = r[t] / R;
+}
+
+// d nodes (zeroed) += scatter; float atomics
+__global__ void interp_weight_bwd_kernel(const float* __restrict__ gw, const float* __restrict__ xyz,
+                                         const float* __restrict__ nodes, const int* __restrict__ idx, int N, int S, int K,
+                                         float* __restrict__ dnodes) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (n >= N) return;
+  const float* xb = xyz + (size_t)b * 3 * N;
+  const float x[3] = {__ldg(xb + n), __ldg(xb + N + n), __ldg(xb + 2 * N + n)};
+  const float xx = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+  float r[8], y[8][3], R = 0.f, gdotw = 0.f;
+  bool clamped[8];
+  int id[8];
+  for (int t = 0; t < K; ++t) {
+    id[t] = __ldg(idx + ((size_t)b * N + n) * K + t);
+    const float* yp = nodes + ((size_t)b * S + id[t]) * 3;
+    y[t][0] = __ldg(yp); y[t][1] = __ldg(yp + 1); y[t][2] = __ldg(yp + 2);
+    const float dot = x[0] * y[t][0] + x[1] * y[t][1] + x[2] * y[t][2];
+    float d = -2.f * dot + xx + (y[t][0] * y[t][0] + y[t][1] * y[t][1] + y[t][2] * y[t][2]);
+    clamped[t] = d < 1e-10f;
+    d = clamped[t] ? 1e-10f : d;
+    r[t] = 1.f / d;
+    R += r[t];
+  }
+  for (int t = 0; t < K; ++t) gdotw += __ldg(gw + ((size_t)b * N + n) * K + t) * (r[t] / R);
+  for (int t = 0; t < K; ++t) {
+    if (clamped[t]) continue;  // the reference's masked assignment cuts the gradient
+    const float dr = (__ldg(gw + ((size_t)b * N + n) * K + t) - gdotw) / R;  // dL/dr_t
+    const float dd = -dr * r[t] * r[t];                                      // dL/dd_t
+    float* o = dnodes + ((size_t)b * S + id[t]) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(o + c, dd * 2.f * (y[t][c] - x[c]));
+  }
+}
+
+}  // namespace sug
+
+extern "C" int sug_node_offset_fwd(const float* h, const float* xyz, const int32_t* fidx, const int32_t* gidx, int B,
+                                   int N, int S, int G, float* out, sug_stream_t stream) {
+  using namespace sug;
+  SUG_CHECK_ARG(h && xyz && fidx && gidx && out && B > 0 && N > 0 && S > 0 && G > 0, "node_offset_fwd: bad argument");
+  ProfScope ps(KC_ADAPT, 12.0 * B * S * G, 4.0 * B * (6.0 * N + S * (G + 4.0)), (cudaStream_t)stream);
+  node_offset_fwd_kernel<<<dim3(cdiv((long long)S * 32, 256), B), 256, 0, (cudaStream_t)stream>>>(h, xyz, fidx, gidx, N, S, G, out);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_node_offset_bwd(const float* gout, const float* h, const float* xyz, const int32_t* fidx,
+                                   const int32_t* gidx, int B, int N, int S, int G, float* dh, sug_stream_t stream) {
+  using namespace sug;
+  SUG_CHECK_ARG(gout && h && xyz && fidx && gidx && dh && B > 0 && N > 0 && S > 0 && G > 0, "node_offset_bwd: bad argument");
+  ProfScope ps(KC_ADAPT, 20.0 * B * S * G, 4.0 * B * (9.0 * N + S * (G + 4.0)), (cudaStream_t)stream);
+  node_offset_bwd_kernel<<<dim3(cdiv((long long)S * 32, 256), B), 256, 0, (cudaStream_t)stream>>>(gout, h, xyz, fidx, gidx, N, S, G, dh);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_interp_weight_fwd(const float* xyz, const float* nodes, const int32_t* idx, int B, int N, int S, int K,
+                                     float* w, sug_stream_t stream) {
+  using namespace sug;
+  SUG_CHECK_ARG(xyz && nodes && idx && w && B > 0 && N > 0 && S > 0 && K > 0 && K <= 8, "interp_weight_fwd: bad argument");
+  ProfScope ps(KC_ADAPT, 20.0 * B * N * K, 4.0 * B * (3.0 * N + 3.0 * S + 2.0 * N * K), (cudaStream_t)stream);
+  interp_weight_fwd_kernel<<<dim3(cdiv(N, 256), B), 256, 0, (cudaStream_t)stream>>>(xyz, nodes, idx, N, S, K, w);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_interp_weight_bwd(const float* gw, const float* xyz, const float* nodes, const int32_t* idx, int B,
+                                     int N, int S, int K, float* dnodes, sug_stream_t stream) {
+  using namespace sug;
+  SUG_CHECK_ARG(gw && xyz && nodes && idx && dnodes && B > 0 && N > 0 && S > 0 && K > 0 && K <= 8, "interp_weight_bwd: bad argument");
+  ProfScope ps(KC_ADAPT, 40.0 * B * N * K, 4.0 * B * (3.0 * N + 6.0 * S + 2.0 * N * K), (cudaStream_t)stream);
+  interp_weight_bwd_kernel<<<dim3(cdiv(N, 256), B), 256, 0, (cudaStream_t)stream>>>(gw, xyz, nodes, idx, N, S, K, dnodes);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}

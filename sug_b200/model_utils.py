@@ -155,21 +155,19 @@ class adapt_layer_off(nn.Module):
 
     def forward_pm(self, fea, input_loc):
         """Point-major core.  fea [B,N,C], input_loc [B,3,N] ->
-        (cat(fea, interpolated) [B,N,2C], node_fea [B,S,C], node_offset [B,S,3])."""
+        (cat(fea, interpolated) [B,N,2C], node_fea [B,S,C], node_offset [B,S,3]).
+        ``input_loc`` is the raw cloud in every reference model; no gradient is propagated to it."""
         B, N, C = fea.shape
         S = self.num_node
         loc = input_loc.transpose(1, 2)  # [B,N,3] view
         bi = torch.arange(B, device=fea.device).view(B, 1)
-        bi3 = bi.view(B, 1, 1)
         fidx = point_utils.farthest_point_sample(input_loc, S)                        # [B,S]
         f_loc = loc[bi, fidx]                                                           # [B,S,3]
         gidx = point_utils.query_ball_point(0.3, 64, input_loc, f_loc.transpose(1, 2))  # [B,S,64]
         # pred_offset is a bias-free 1x1 conv, i.e. linear: W (fea[g] - fea[f]) = (W fea)[g] - (W fea)[f],
         # so the 64 -> 3 map runs once per point and only 3-vectors are gathered (model_utils.py:112-113)
         h = ops.linear(fea, self.pred_offset[0].weight)                                # [B,N,3]
-        seman_trans = torch.tanh(h[bi3, gidx] - h[bi, fidx].unsqueeze(2))              # [B,S,64,3]
-        g_loc = loc[bi3, gidx] - f_loc.unsqueeze(2)                                     # [B,S,64,3]
-        node_offset = (seman_trans * g_loc).mean(dim=2)                                 # [B,S,3]
+        node_offset = ops.node_offset(h, input_loc, fidx, gidx)                         # [B,S,3] (lines 107-117, fused)
         node_loc = f_loc + node_offset
         node_loc_cm = node_loc.transpose(1, 2)                                          # [B,3,S]
         gidx2 = ops.knn_query(input_loc, node_loc_cm, 64, ordered=False)               # [B,S,64] (a set)
@@ -177,12 +175,7 @@ class adapt_layer_off(nn.Module):
         node_fea = ops.group_max(residual_fea, gidx2)                                   # [B,S,C]
         # 3-NN inverse-squared-distance interpolation back to the points (point_utils.py:134-165)
         idx3 = ops.three_nn(input_loc, node_loc_cm, 3)                                  # [B,N,3] int32
-        nb = node_loc[bi3, idx3.long()]                                                 # [B,N,3,3]
-        dots = (loc.unsqueeze(2) * nb).sum(-1)
-        dists = -2 * dots + (loc ** 2).sum(-1, keepdim=True) + (nb ** 2).sum(-1)
-        dists = torch.where(dists < 1e-10, torch.full_like(dists, 1e-10), dists)
-        weight = 1.0 / dists
-        weight = weight / weight.sum(dim=-1, keepdim=True)
+        weight = ops.interp_weights(input_loc, node_loc, idx3)                          # [B,N,3]
         interp = ops.interpolate(node_fea, idx3, weight)                                # [B,N,C]
         return torch.cat((fea, interp), dim=2), node_fea, node_offset
 

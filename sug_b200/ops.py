@@ -528,6 +528,76 @@ def interpolate(f, idx, w):
     return _InterpFn.apply(f, idx.int().contiguous(), w)
 
 
+class _NodeOffsetFn(torch.autograd.Function):
+    """h [B,N,3], xyz [B,3,N], fidx int32 [B,S], gidx int32 [B,S,G] -> mean_j tanh(h[g_j]-h[f]) * (xyz[g_j]-xyz[f])."""
+
+    @staticmethod
+    def forward(ctx, h, xyz, fidx, gidx):
+        h = h.float().contiguous()
+        B, N, _ = h.shape
+        S, G = gidx.shape[1], gidx.shape[2]
+        out = torch.empty(B, S, 3, dtype=torch.float32, device=h.device)
+        lib = _lib.load()
+        with torch.cuda.device(h.device):
+            _lib.check(lib.sug_node_offset_fwd(_ptr(h), _ptr(xyz), _ptr(fidx), _ptr(gidx), B, N, S, G, _ptr(out), _stream()),
+                       "sug_node_offset_fwd")
+        ctx.save_for_backward(h, xyz, fidx, gidx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, xyz, fidx, gidx = ctx.saved_tensors
+        B, N, _ = h.shape
+        S, G = gidx.shape[1], gidx.shape[2]
+        dh = torch.zeros_like(h)
+        lib = _lib.load()
+        with torch.cuda.device(h.device):
+            _lib.check(lib.sug_node_offset_bwd(_ptr(g.float().contiguous()), _ptr(h), _ptr(xyz), _ptr(fidx), _ptr(gidx), B, N, S, G,
+                                               _ptr(dh), _stream()), "sug_node_offset_bwd")
+        return dh, None, None, None
+
+
+def node_offset(h, xyz, fidx, gidx):
+    """model_utils.py:107-117 after pred_offset has been applied per point (it is linear and bias-free)."""
+    _need_cuda(h, xyz, fidx, gidx)
+    return _NodeOffsetFn.apply(h, _xyz(xyz), fidx.int().contiguous(), gidx.int().contiguous())
+
+
+class _InterpWeightFn(torch.autograd.Function):
+    """xyz [B,3,N], nodes [B,S,3], idx int32 [B,N,K] -> normalised inverse squared distances [B,N,K]."""
+
+    @staticmethod
+    def forward(ctx, xyz, nodes, idx):
+        nodes = nodes.float().contiguous()
+        B, _, N = xyz.shape
+        S, K = nodes.shape[1], idx.shape[2]
+        w = torch.empty(B, N, K, dtype=torch.float32, device=nodes.device)
+        lib = _lib.load()
+        with torch.cuda.device(nodes.device):
+            _lib.check(lib.sug_interp_weight_fwd(_ptr(xyz), _ptr(nodes), _ptr(idx), B, N, S, K, _ptr(w), _stream()),
+                       "sug_interp_weight_fwd")
+        ctx.save_for_backward(xyz, nodes, idx)
+        return w
+
+    @staticmethod
+    def backward(ctx, g):
+        xyz, nodes, idx = ctx.saved_tensors
+        B, _, N = xyz.shape
+        S, K = nodes.shape[1], idx.shape[2]
+        dn = torch.zeros_like(nodes)
+        lib = _lib.load()
+        with torch.cuda.device(nodes.device):
+            _lib.check(lib.sug_interp_weight_bwd(_ptr(g.float().contiguous()), _ptr(xyz), _ptr(nodes), _ptr(idx), B, N, S, K,
+                                                 _ptr(dn), _stream()), "sug_interp_weight_bwd")
+        return None, dn, None
+
+
+def interp_weights(xyz, nodes, idx):
+    """point_utils.py:141-160: weights of the k-NN inverse-squared-distance interpolation; gradients flow to ``nodes``."""
+    _need_cuda(xyz, nodes, idx)
+    return _InterpWeightFn.apply(_xyz(xyz), nodes, idx.int().contiguous())
+
+
 def three_nn(xyz, nodes, k: int = 3) -> torch.Tensor:
     xyz, nodes = _xyz(xyz), _xyz(nodes)
     B, _, N = xyz.shape
