@@ -140,7 +140,8 @@ class Pointnet_c(nn.Module):
             x = self.dropout1(self.mlp1(x))
         x = self.mlp2(x)
         mid_feature = x
-        x = self.mlp3(self.dropout2(x))
+        x = self.dropout2(x)
+        x = ops.linear(x, self.mlp3.weight, self.mlp3.bias) if x.is_cuda else self.mlp3(x)
         if adapt is False or adapt == False:  # noqa: E712  (reference compares with ==)
             return x
         return x, mid_feature

@@ -100,6 +100,11 @@ class fc_layer(nn.Module):
             self.fc = nn.Sequential(nn.Linear(in_ch, out_ch, bias=bias), self.ac)
 
     def forward(self, x):
+        if x.is_cuda:  # the library's fp32-accurate GEMM instead of a cuBLAS SIMT kernel picked for M = batch
+            y = ops.linear(x, self.fc[0].weight, self.fc[0].bias)
+            for m in list(self.fc)[1:]:
+                y = m(y)
+            return y
         return self.fc(x)
 
 
