@@ -587,6 +587,43 @@ def test_full_size_properties(S):
     assert int(blk.conv[1].num_batches_tracked) == 2
 
 
+def test_node_offset_and_interp_weights(S):
+    """Fused adapt-layer pieces against their tensor-op spelling (model_utils.py:107-117,
+    point_utils.py:141-160) in fp64, values and gradients."""
+    torch.manual_seed(11)
+    B, N, Sn, G = 3, 200, 16, 24
+    xyz = torch.rand(B, 3, N, device=DEV) * 2 - 1
+    h = torch.randn(B, N, 3, device=DEV, requires_grad=True)
+    fidx = torch.stack([torch.randperm(N, device=DEV)[:Sn] for _ in range(B)])
+    gidx = torch.randint(0, N, (B, Sn, G), device=DEV)
+    out = S.ops.node_offset(h, xyz, fidx, gidx)
+    go = torch.randn_like(out)
+    out.backward(go)
+    hd = h.detach().double().requires_grad_(True)
+    loc = xyz.double().transpose(1, 2)
+    bi = torch.arange(B, device=DEV).view(B, 1)
+    ref = (torch.tanh(hd[bi.view(B, 1, 1), gidx] - hd[bi, fidx].unsqueeze(2))
+           * (loc[bi.view(B, 1, 1), gidx] - loc[bi, fidx].unsqueeze(2))).mean(dim=2)
+    ref.backward(go.double())
+    assert_close(out.detach(), ref.detach(), 1e-5, "node_offset")
+    assert_close(h.grad, hd.grad, 1e-5, "node_offset dh")
+
+    nodes = (torch.rand(B, Sn, 3, device=DEV) * 2 - 1).requires_grad_(True)
+    idx3 = S.ops.three_nn(xyz, nodes.detach().transpose(1, 2).contiguous(), 3)
+    w = S.ops.interp_weights(xyz, nodes, idx3)
+    gw = torch.randn_like(w)
+    w.backward(gw)
+    nd = nodes.detach().double().requires_grad_(True)
+    nb = nd[bi.view(B, 1, 1), idx3.long()]
+    d = -2 * (loc.unsqueeze(2) * nb).sum(-1) + (loc ** 2).sum(-1, keepdim=True) + (nb ** 2).sum(-1)
+    d = torch.where(d < 1e-10, torch.full_like(d, 1e-10), d)
+    wr = 1.0 / d
+    wr = wr / wr.sum(-1, keepdim=True)
+    wr.backward(gw.double())
+    assert_close(w.detach(), wr.detach(), 1e-4, "interp weights")
+    assert_close(nodes.grad, nd.grad, 2e-4, "interp weights dnodes")
+
+
 def test_fused_adam_matches_torch(S):
     """optim.FusedAdam (one multi-tensor launch) against torch.optim.Adam: weight decay, a parameter
     without gradient, odd sizes, an LR change between steps."""
