@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-all", action="store_true", help="time every kernel class (diagnostics)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
+    ap.add_argument("--share-trunk", action="store_true",
+                    help="NOT the headline configuration: let the second encoder pass on a batch reuse conv1/conv2 of the "
+                         "first (DGCNN.share_trunk); the default times the four full forwards the reference runs")
     return ap.parse_args()
 
 
@@ -192,6 +195,7 @@ def _main(args, rank, emit):
 
     torch.manual_seed(666)  # train_dg_single_gpu.py:65
     model = Model.Net_MDA("DGCNN").to(dev).train()
+    model.g.share_trunk = bool(args.share_trunk)
     opts = step.make_optimizers(model, capturable=not args.no_graph)
     crit = model_utils.focal_loss(num_classes=10, gamma=0.0, alpha=[0.1] * 10)  # ClassWeighting / DLSA, uniform counts
     mmd_fn = sdist.global_mmd_cal if (args.mmd_scope == "global" and world > 1) else None
@@ -350,6 +354,7 @@ def _main(args, rank, emit):
                                    "(DG_unified_loss_onedataset_shapenet.yaml)",
                        "clouds_per_step_per_gpu": 2 * B, "batch_per_subdomain": B, "points": N_POINTS, "k": 20,
                        "classes": 10, "parallelism": f"dp{world}", "mmd_scope": args.mmd_scope, "execution": mode,
+                       "shared_trunk": bool(args.share_trunk),
                        "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

@@ -7,6 +7,8 @@ Out of scope (other model families): Pointnet2_g, PTran
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -66,6 +68,49 @@ class DGCNN(nn.Module):
         self.node_fea_adapt = adapt_layer_off()
         self.conv1d = nn.Conv1d(128, 64, 1)
         self.dim_redu = nn.MaxPool1d(3, stride=16)
+        # Opt-in (off by default; env SUG_B200_SHARE_TRUNK=1 or ``share_trunk = True``): the SUG step runs
+        # this encoder TWICE on every cloud batch (train_dg_single_gpu.py:260-261 and 297-298).  Everything
+        # before the adapt layer (two kNN graphs, conv1, conv2) is a deterministic function of the input
+        # and the weights -- only the FPS start of the node layer differs between the two passes -- so in
+        # training mode the second pass may reuse x1 / x2 of the first.  BatchNorm side effects are replayed
+        # (second momentum update with the same batch statistics, num_batches_tracked).  bench.py's headline
+        # number does NOT use this (it times the four full forwards the reference runs).
+        self.share_trunk = os.environ.get("SUG_B200_SHARE_TRUNK", "0") == "1"
+        self._trunk = {}  # key -> (x1, x2, batch statistics of conv1 / conv2); at most two batches (source, target)
+
+    def _trunk_key(self, x):
+        ps = (self.conv1.conv[0].weight, self.conv1.conv[1].weight, self.conv1.conv[1].bias,
+              self.conv2.conv[0].weight, self.conv2.conv[1].weight, self.conv2.conv[1].bias)
+        return (x.data_ptr(), x._version, tuple(x.shape), torch.is_grad_enabled(), tuple(p._version for p in ps))
+
+    def _trunk_fwd(self, x_loc, x0):
+        """x1, x2 of Model.py:88-94 (and nothing else)."""
+        k = self.k
+        if not (self.share_trunk and self.training):
+            x1 = self.conv1.edgeconv(x0, ops.knn_cm(x_loc, k))
+            return x1, self.conv2.edgeconv(x1, ops.knn_pm(x1, k))
+        key = self._trunk_key(x_loc)
+        hit = self._trunk.pop(key, None)  # one reuse per batch: the pair of passes of one step
+        if hit is not None:
+            x1, x2, stats = hit
+            with torch.no_grad():
+                for bn, (s_m, s_v) in zip((self.conv1.conv[1], self.conv2.conv[1]), stats):
+                    m = bn.momentum
+                    bn.running_mean.mul_(1 - m).add_(s_m, alpha=m)  # the same batch statistics once more
+                    bn.running_var.mul_(1 - m).add_(s_v, alpha=m)
+                    bn.num_batches_tracked.add_(1)
+            return x1, x2
+        if len(self._trunk) >= 2:
+            self._trunk.clear()
+        bns = (self.conv1.conv[1], self.conv2.conv[1])
+        before = [(bn.running_mean.clone(), bn.running_var.clone()) for bn in bns]
+        x1 = self.conv1.edgeconv(x0, ops.knn_cm(x_loc, k))
+        x2 = self.conv2.edgeconv(x1, ops.knn_pm(x1, k))
+        with torch.no_grad():  # r1 = (1-m) r0 + m s  =>  s, the batch statistic this pass folded in
+            stats = [((bn.running_mean - (1 - bn.momentum) * rm0) / bn.momentum,
+                      (bn.running_var - (1 - bn.momentum) * rv0) / bn.momentum) for bn, (rm0, rv0) in zip(bns, before)]
+        self._trunk[key] = (x1, x2, stats)
+        return x1, x2
 
     def _tail(self, x_cat):
         bn = self.bn5
@@ -79,8 +124,7 @@ class DGCNN(nn.Module):
         B = x.size(0)
         k = self.k
         x0 = x_loc.transpose(1, 2).contiguous()  # point-major [B,N,3]
-        x1 = self.conv1.edgeconv(x0, ops.knn_cm(x_loc, k))
-        x2 = self.conv2.edgeconv(x1, ops.knn_pm(x1, k))
+        x1, x2 = self._trunk_fwd(x_loc, x0)
         x_, node_pm, _ = self.node_fea_adapt.forward_pm(x2, x_loc)           # [B,N,128], [B,64 nodes,64]
         node_fea = node_pm.transpose(1, 2).unsqueeze(3)                       # reference layout [B,64,64,1]
         x2 = ops.linear(x_, self.conv1d.weight, self.conv1d.bias)             # Conv1d(128,64,1) on point-major rows

@@ -163,7 +163,9 @@ def test_knn_golden(S, golden, C, N):
 
 
 @pytest.mark.parametrize("B,C,N,k,layout", [(4, 3, 1024, 20, "cm"), (4, 64, 1024, 20, "pm"), (2, 128, 1024, 40, "pm"),
-                                            (3, 3, 1000, 20, "cm"), (2, 64, 333, 20, "pm"), (1, 7, 50, 50, "cm")])
+                                            (3, 3, 1000, 20, "cm"), (2, 64, 333, 20, "pm"), (1, 7, 50, 50, "cm"),
+                                            (2, 16, 128, 20, "pm"), (1, 32, 2000, 20, "pm"), (2, 64, 777, 40, "pm"),
+                                            (2, 96, 640, 20, "pm"), (3, 64, 20, 20, "pm")])
 def test_knn_oracle(S, B, C, N, k, layout):
     x = O.synth_clouds(B, N, 3)[0].squeeze(-1) if C == 3 else feat_input(B, C, N, 5)
     if layout == "cm":
@@ -177,6 +179,27 @@ def test_knn_oracle(S, B, C, N, k, layout):
     assert n_diff <= max(2, int(2e-3 * B * N))
     if N >= k and C == 3:
         assert bool((idx[..., 0].cpu() == torch.arange(N).view(1, N)).all()), "self must be neighbour 0"
+
+
+def test_knn_duplicates_and_strided_rows(S):
+    """Exact ties (duplicated points) must still give k distinct neighbours with the top-k distances, and
+    a channel slice of a wider point-major buffer is a legal operand."""
+    B, C, N, k = 2, 64, 512, 20
+    x = feat_input(B, C, N, 77)                      # [B,C,N]
+    x[:, :, 100:140] = x[:, :, 60:61]                # 41 identical points
+    xpm = x.transpose(1, 2).contiguous().to(DEV)
+    idx = S.ops.knn_pm(xpm, k)
+    assert int(idx.min()) >= 0 and int(idx.max()) < N
+    srt = idx.sort(-1)[0]
+    assert bool((srt[..., 1:] != srt[..., :-1]).all()), "duplicate neighbour index"
+    D = O.pairwise_neg_sqdist(x)
+    ref_d = D.topk(k, dim=-1)[0]
+    got_d = torch.gather(D, 2, idx.cpu().long()).sort(-1, descending=True)[0]
+    assert float((ref_d - got_d).abs().max()) <= 1e-4 * float(D.abs().max())
+    wide = torch.randn(B, N, 256, device=DEV)
+    wide[:, :, 64:128] = xpm
+    idx2 = S.ops.knn_pm(wide[:, :, 64:128], k)
+    assert torch.equal(idx2.sort(-1)[0], srt)
 
 
 def test_knn_reverse(S):
@@ -699,6 +722,39 @@ def test_graphed_step_matches_eager(S):
     pe, pg = dict(net_e.named_parameters()), dict(net_g.named_parameters())
     for k in ("g.conv1.conv.0.weight", "g.conv5.weight", "c1.mlp3.weight", "attention_s.bn.weight"):
         assert relerr(pg[k], pe[k]) < 1e-2, k
+
+
+def test_shared_trunk_matches_four_full_forwards(S):
+    """Opt-in DGCNN.share_trunk: the second pass on a batch reuses conv1 / conv2 of the first.  Losses,
+    gradients, BatchNorm running statistics and counters must equal the four full forwards."""
+    B = 12
+    d, l = O.synth_clouds(B, 512, 30)
+    dt, lt = O.synth_clouds(B, 512, 31)
+    batch = tuple(t.to(DEV) for t in (d, l, dt, lt))
+    res = []
+    for share in (False, True):
+        net = _load(S.Model.Net_MDA("DGCNN"), "Net_MDA:DGCNN").train()
+        net.g.share_trunk = share
+        crit = S.model_utils.focal_loss(num_classes=10, gamma=0.0, alpha=[0.1] * 10)
+        torch.manual_seed(9)
+        out = S.step.sug_losses(net, *batch, crit)
+        out["loss"].backward()
+        res.append((net, out))
+    (n0, o0), (n1, o1) = res
+    for key in ("loss", "loss_cls", "loss_geo", "loss_sem"):
+        assert abs(float(o0[key]) - float(o1[key])) <= 2e-5 * max(1e-3, abs(float(o0[key]))), key
+    g0 = {k: p.grad for k, p in n0.named_parameters() if p.grad is not None}
+    g1 = {k: p.grad for k, p in n1.named_parameters() if p.grad is not None}
+    assert g0.keys() == g1.keys()
+    gmax = max(float(v.abs().max()) for v in g0.values())
+    for k in g0:
+        err = float((g0[k] - g1[k]).abs().max()) / max(float(g0[k].abs().max()), 1e-4 * gmax)
+        assert err < 2e-3, (k, err)
+    for name in ("conv1", "conv2", "conv3"):
+        b0, b1 = getattr(n0.g, name).conv[1], getattr(n1.g, name).conv[1]
+        assert_close(b1.running_mean, b0.running_mean, 1e-4, name + " running_mean")
+        assert_close(b1.running_var, b0.running_var, 1e-4, name + " running_var")
+        assert int(b1.num_batches_tracked) == int(b0.num_batches_tracked) == 4
 
 
 def test_lidar_scale_inference(S):
