@@ -150,12 +150,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
   uint64_t* full = bars;             // [S] TMA -> split
   uint64_t* ready = bars + S;        // [S] split -> MMA
   uint64_t* empty = bars + 2 * S;    // [S] MMA -> TMA
-  uint64_t* tfull = bars + 3 * S;    // [2] MMA -> selection
-  uint64_t* tempty = bars + 3 * S + 2;  // [2] selection -> MMA
-  uint64_t* a_full = bars + 3 * S + 4;  // TMA(A) -> split
-  uint64_t* a_ready = bars + 3 * S + 5; // split -> MMA, TMA   (A hi/lo are in TMEM, staging is free)
-  uint64_t* a_free = bars + 3 * S + 6;  // MMA -> TMA          (all MMAs of the query block retired)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 7);
+  uint64_t* tfull = bars + 3 * S;    // [3] MMA -> selection
+  uint64_t* tempty = bars + 3 * S + 3;  // [3] selection -> MMA
+  uint64_t* a_full = bars + 3 * S + 6;  // TMA(A) -> split
+  uint64_t* a_ready = bars + 3 * S + 7; // split -> MMA, TMA   (A hi/lo are in TMEM, staging is free)
+  uint64_t* a_free = bars + 3 * S + 8;  // MMA -> TMA          (all MMAs of the query block retired)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 9);
   float* xxs = reinterpret_cast<float*>(smem + L::xxs);
   float* tbuf = reinterpret_cast<float*>(smem + L::tbuf);
   int* cnts = reinterpret_cast<int*>(smem + L::cnts);
@@ -165,7 +165,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_m = p.B * p.mtiles_per_cloud;
   const int kbs = (p.C + 31) / 32;
-  constexpr uint32_t A_COL = 2 * QBN;  // TMEM: [0,256) two accumulators, then 64 columns (hi|lo) per slab
+  // TMEM: nacc accumulators of 128 columns, then 64 columns (hi|lo) per query slab.  A group is bound to the
+  // tiles of one parity; with only two accumulators the MMA of its next tile cannot start before the group
+  // has drained the current one (cycle = select + MMA).  Three accumulators (C <= 64: 3*128 + 2*64 = 512
+  // columns) let the MMA run one tile further ahead, so a group finds its next tile ready.
+  const uint32_t nacc = kbs <= 2 ? 3u : 2u;
+  const uint32_t A_COL = nacc * QBN;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
@@ -174,7 +179,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
       mbar_init(&ready[s], 128);
       mbar_init(&empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 3; ++b) {
       mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], 128);
     }
@@ -228,8 +233,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
         mbar_wait(a_ready, mi & 1);
         tc_fence_after();
         for (int t = 0; t < 2 * p.ntiles; ++t, ++tile_it) {
-          const int ab = tile_it & 1;
-          mbar_wait(&tempty[ab], ((tile_it >> 1) & 1) ^ 1);
+          const uint32_t ab = tile_it % nacc;
+          mbar_wait(&tempty[ab], ((tile_it / nacc) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tacc = tmem_base + ab * QBN;
           for (int kb = 0; kb < kbs; ++kb, ++it) {
@@ -364,14 +369,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
         if (t >= 2 * p.ntiles) break;
         const bool sweep1 = t >= p.ntiles;
         const int nt = sweep1 ? t - p.ntiles : t;
-        const int ab = grp;
         const uint32_t my_it = tile_it + (uint32_t)t;
+        const uint32_t ab = my_it % nacc;
         float* gx = gxx + nbuf * (2 * QBN);  // double-buffered norms: one group barrier per tile
         gx[gt] = nx;
         nx = load_norm(t + 2);  // in flight while this tile is processed
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
-        mbar_wait(&tfull[ab], (my_it >> 1) & 1);
+        mbar_wait(&tfull[ab], (my_it / nacc) & 1);
         tc_fence_after();
         const int nh = min(QBN / 16, (p.N - nt * QBN + 15) >> 4);  // 16-candidate half chunks in this tile
         const uint32_t tsrc = tmem_base + ((uint32_t)(lg * 32) << 16) + ab * QBN;
