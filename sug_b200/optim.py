@@ -126,11 +126,15 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.load()
-        capturing = torch.cuda.is_current_stream_capturing()
+        capturing = None
         for gi, group in enumerate(self.param_groups):
             first = next((p for p in group["params"] if p.grad is not None), None)
             if first is None:
                 continue
+            if not first.is_cuda:
+                raise RuntimeError("FusedAdam runs on contiguous fp32 CUDA parameters only (there is no CPU fallback)")
+            if capturing is None:
+                capturing = torch.cuda.is_current_stream_capturing()
             gs = self._group_state(gi, group, first.device)
             if not capturing:
                 self.sync_lr()

@@ -90,3 +90,30 @@ def test_unsupported_backbones_are_explicit():
     for n in ("Pointnet2", "PTran", "KPConv"):
         with pytest.raises(NotImplementedError):
             Model.Net_MDA(n)
+
+
+def test_fused_adam_has_no_cpu_path_and_mirrors_adam_groups():
+    """optim.FusedAdam keeps torch.optim.Adam's param_groups / hyper-parameters, refuses CPU parameters
+    (no CPU fallback) and exports its chunk size through the C ABI."""
+    from sug_b200 import _lib
+    from sug_b200.optim import FusedAdam
+    assert _lib.load().sug_adam_chunk() >= 1024
+    p = torch.nn.Parameter(torch.zeros(8))
+    opt = FusedAdam([{"params": [p], "lr": 3e-3}], lr=1e-3, weight_decay=5e-4)
+    g = opt.param_groups[0]
+    assert g["lr"] == 3e-3 and g["betas"] == (0.9, 0.999) and g["eps"] == 1e-8 and g["weight_decay"] == 5e-4
+    opt.step()  # no gradient yet: a no-op like torch.optim.Adam
+    p.grad = torch.ones(8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        opt.step()
+    with pytest.raises(ValueError):
+        FusedAdam([p], lr=-1.0)
+
+
+def test_shared_trunk_is_opt_in():
+    """The common-subexpression switch of DGCNN must be off unless asked for."""
+    import os
+    from sug_b200 import Model
+    assert os.environ.get("SUG_B200_SHARE_TRUNK", "0") != "1"
+    net = Model.Net_MDA("DGCNN")
+    assert net.g.share_trunk is False and net.g._trunk == {}
