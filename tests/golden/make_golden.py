@@ -25,7 +25,12 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 warnings.simplefilter("ignore")
 
 
+ONLY = None  # set by --only NAME: write just that fixture
+
+
 def npz(name, **arrs):
+    if ONLY is not None and name != ONLY:
+        return
     conv = {}
     for k, v in arrs.items():
         if isinstance(v, torch.Tensor):
@@ -128,6 +133,19 @@ def main():
         pf, pnode, poff = pn.g(x, node=True)
         npz("pointnet_g", feat=pf, node_fea=pnode, node_off=poff, rv5=pn.g.conv5.conv[1].running_var)
 
+        # ---- Net_MDA('Pointnet') modes (Model.py:485-520): eval logits, train-mode node branches ---
+        pn2 = load_ref_module(R.Model.Net_MDA("Pointnet"), "Net_MDA:Pointnet", seed=668)
+        pn2.eval()
+        with torch.no_grad():
+            torch.manual_seed(21)
+            e1, e2 = pn2(x)
+        pn2.train()
+        torch.manual_seed(22)
+        pns = pn2(x, node_adaptation_s=True)
+        torch.manual_seed(23)
+        pnt = pn2(x, node_adaptation_t=True)
+        npz("net_mda_pointnet", y1_eval=e1, y2_eval=e2, node_s=pns, node_t=pnt)
+
         # ---- MMD (mmd.py) --------------------------------------------------------------------
         rng = np.random.Generator(np.random.PCG64(51))
         m = 16
@@ -193,4 +211,6 @@ def main():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) == 3 and sys.argv[1] == "--only":
+        ONLY = sys.argv[2]
     main()

@@ -504,6 +504,23 @@ def test_net_mda_golden(S, golden):
         assert_close(nt, g["node_t"], 1e-3, "node_t vs fixture")
 
 
+def test_net_mda_pointnet_golden(S, golden):
+    """Net_MDA('Pointnet') against the fixture of the unmodified reference: eval logits, node branches."""
+    g = golden("net_mda_pointnet")
+    x, _ = O.synth_clouds(2, 1024, 41)
+    net = _load(S.Model.Net_MDA("Pointnet"), "Net_MDA:Pointnet", 668).eval()
+    with torch.no_grad():
+        torch.manual_seed(21)
+        y1, y2 = net(x.to(DEV))
+    assert_close(y1, g["y1_eval"], 1e-3, "pointnet y1 eval")
+    assert_close(y2, g["y2_eval"], 1e-3, "pointnet y2 eval")
+    net.train()
+    torch.manual_seed(22)
+    assert_close(net(x.to(DEV), node_adaptation_s=True), g["node_s"], 1e-3, "pointnet node_s")
+    torch.manual_seed(23)
+    assert_close(net(x.to(DEV), node_adaptation_t=True), g["node_t"], 1e-3, "pointnet node_t")
+
+
 def test_dgcnn_cls_golden(S, golden):
     x, _ = O.synth_clouds(2, 1024, 41)
     cls = _load(S.model_pointnet.DGCNN(), "DGCNN_cls", 667).eval()

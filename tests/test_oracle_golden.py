@@ -112,6 +112,22 @@ def test_pointnet_g(golden):
     close(sd["g.conv5.conv.1.running_var"], g["rv5"], 1e-4, 1e-6)
 
 
+def test_net_mda_pointnet(golden):
+    """Net_MDA('Pointnet') (Model.py:485-520): eval-mode logits of both heads, train-mode node branches."""
+    g = golden("net_mda_pointnet")
+    x, _ = O.synth_clouds(2, 1024, 41)
+    sd = O.synth_state("Net_MDA:Pointnet", 668)
+    with torch.no_grad():
+        torch.manual_seed(21)
+        y1, y2 = O.net_mda(x, sd, False, model_name="Pointnet")
+    close(y1, g["y1_eval"], 1e-3, 1e-4)
+    close(y2, g["y2_eval"], 1e-3, 1e-4)
+    torch.manual_seed(22)
+    close(O.net_mda(x, sd, True, model_name="Pointnet", node_adaptation_s=True), g["node_s"], 1e-3, 1e-4)
+    torch.manual_seed(23)
+    close(O.net_mda(x, sd, True, model_name="Pointnet", node_adaptation_t=True), g["node_t"], 1e-3, 1e-4)
+
+
 def mmd_inputs():
     rng = np.random.Generator(np.random.PCG64(51))
     m = 16
