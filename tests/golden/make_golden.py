@@ -174,6 +174,18 @@ def main():
         npz("mmd", v_plain=v_plain, v_w=v_w, dX=Xg.grad, dY=Yg.grad, v_sem=v_sem_plain, dXs=Xsg.grad, dYs=Ysg.grad,
             geo_w=geo_w, sem_w=sem_w, geo=geo, sem=sem, cd1=cd1, cd2=cd2)
 
+        # ---- the MMD modes the SUG config does not use (mmd.py:25-41, 69-77, 178-202, 274-312) ---
+        lt_same = ls.clone()
+        lt_same[::3] = (lt_same[::3] + 1) % 10  # about two thirds of the pairs share their label
+        hard = R.mmd.mmd_cal(ls, Xs, lt_same, Ys, {"NAME": "HARD_MMD"})
+        off = R.mmd.mmd_cal(ls, Xs, lt, Ys, {"NAME": "OFF"})
+        unb = R.mmd.mix_rbf_mmd2(Xs, Ys, R.mmd.sigma_list, biased=False)
+        cdv = R.mmd.cd_distance(ds.squeeze(-1).transpose(1, 2), dt.squeeze(-1).transpose(1, 2), ref_harness._BruteChamfer())
+        # ("naive_inverse" / "exp_inverse" build Python lists and crash at mmd.py:202 in the reference)
+        w_none = R.mmd.distance2weights(cdv, method="none")
+        geo_none = R.mmd.geometric_weights(ds, dt, weighting="none")
+        npz("mmd_modes", hard=hard, off=off, unbiased=unb, lt_same=lt_same, cd=cdv, w_none=w_none, geo_none=geo_none)
+
         # ---- whole SUG step (train_dg_single_gpu.py:260-329), B=12, dropout off ----------------
         Bs = 12  # >= 10: the reference focal_loss re-gathers its own alpha (model_utils.py:168)
         data, label = O.synth_clouds(Bs, 1024, 0)

@@ -377,6 +377,24 @@ def test_mmd_golden(S, golden):
     assert_close(c2, g["cd2"], 1e-5, "chamfer d2")
 
 
+def test_mmd_modes_golden(S, golden):
+    """The mmd_cal / weighting modes the SUG config does not exercise, against the unmodified reference:
+    HARD_MMD, OFF, the unbiased estimator, weighting 'none' (mmd.py:25-41, 69-77, 178-202, 274-312)."""
+    g = golden("mmd_modes")
+    X, Y, Xs, Ys, ls, lt, w, ps, pt, ds, dt = _mmd_inputs()
+    d = lambda t: t.to(DEV)
+    lt_same = torch.from_numpy(g["lt_same"].astype(np.int64))
+    assert_close(S.mmd.mmd_cal(d(ls), d(Xs), d(lt_same), d(Ys), {"NAME": "HARD_MMD"}), g["hard"], 1e-4, "hard mmd")
+    assert_close(S.mmd.mmd_cal(d(ls), d(Xs), d(lt), d(Ys), {"NAME": "OFF"}), g["off"], 1e-4, "mmd off")
+    assert_close(S.mmd.mix_rbf_mmd2(d(Xs), d(Ys), S.mmd.sigma_list, biased=False), g["unbiased"], 1e-4, "unbiased mmd")
+    cd = S.mmd.cd_distance(d(ds).squeeze(-1).transpose(1, 2), d(dt).squeeze(-1).transpose(1, 2))
+    assert_close(cd, g["cd"], 1e-5, "cd_distance")
+    assert_close(S.mmd.distance2weights(cd, method="none"), g["w_none"], 1e-5, "weights none")
+    assert_close(S.mmd.geometric_weights(d(ds), d(dt), weighting="none"), g["geo_none"], 1e-5, "geo weights none")
+    with pytest.raises(RuntimeError):
+        S.mmd.mmd_cal(d(ls), d(Xs), d(lt), d(Ys), {"NAME": "LINEAR"})
+
+
 def test_mmd_unbiased_and_sizes(S):
     rng = np.random.Generator(np.random.PCG64(5))
     for m, D in ((64, 4106), (64, 266), (7, 33)):
