@@ -174,6 +174,30 @@ def main():
         npz("mmd", v_plain=v_plain, v_w=v_w, dX=Xg.grad, dY=Yg.grad, v_sem=v_sem_plain, dXs=Xsg.grad, dYs=Ysg.grad,
             geo_w=geo_w, sem_w=sem_w, geo=geo, sem=sem, cd1=cd1, cd2=cd2)
 
+        # ---- the public helper functions as users call them (reference layouts) -----------------------
+        # model_utils.get_graph_feature (188-210), point_utils.{index_points, query_ball_point, upsample_inter,
+        # square_distance} (60-165), focal_loss with gamma = 2 and its alpha statefulness (131-176)
+        xa = feat_input(2, 8, 64, 71)
+        gf = R.model_utils.get_graph_feature(xa, k=5)
+        pc = O.synth_clouds(2, 128, 72)[0].squeeze(-1)                      # [2,3,128]
+        torch.manual_seed(73)
+        fi = R.point_utils.farthest_point_sample(pc, 16)
+        ctr = R.point_utils.index_points(pc, fi)                            # [2,3,16]
+        qb = R.point_utils.query_ball_point(0.3, 8, pc, ctr)
+        qk = R.point_utils.query_ball_point(None, 8, pc, ctr)
+        grp = R.point_utils.index_points(pc, qb)                            # [2,3,16,8]
+        nodes_f = feat_input(2, 32, 16, 74)
+        up = R.point_utils.upsample_inter(pc, ctr, None, nodes_f, 3)
+        sqd = R.point_utils.square_distance(pc, ctr)                        # [2,128,16]
+        fl = R.model_utils.focal_loss(num_classes=10, gamma=2, alpha=[0.05 * (i + 1) for i in range(10)], size_average=False)
+        rngf = np.random.Generator(np.random.PCG64(75))
+        lg = torch.from_numpy(rngf.standard_normal((12, 10)).astype(np.float32) * 2)
+        lb = torch.from_numpy(rngf.integers(0, 10, 12).astype(np.int64))
+        f1 = fl(lg, lb)
+        f2 = fl(lg * 0.5, (lb + 3) % 10)  # second call: alpha has been re-gathered by the first (line 168)
+        npz("api_funcs", graph_feature=gf, fps=fi, centres=ctr, ball=qb, knn8=qk, grouped=grp, upsample=up, sqdist=sqd,
+            focal1=f1, focal2=f2)
+
         # ---- the MMD modes the SUG config does not use (mmd.py:25-41, 69-77, 178-202, 274-312) ---
         lt_same = ls.clone()
         lt_same[::3] = (lt_same[::3] + 1) % 10  # about two thirds of the pairs share their label

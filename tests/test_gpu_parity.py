@@ -377,6 +377,35 @@ def test_mmd_golden(S, golden):
     assert_close(c2, g["cd2"], 1e-5, "chamfer d2")
 
 
+def test_api_functions_golden(S, golden):
+    """The helper functions in the reference's own layouts, against outputs of the unmodified reference:
+    get_graph_feature, farthest_point_sample (same CPU RNG draw), index_points, query_ball_point (radius and
+    k-NN form), upsample_inter, square_distance, focal_loss (gamma = 2, sum reduction, alpha re-gathered)."""
+    g = golden("api_funcs")
+    d = lambda t: t.to(DEV)
+    xa = feat_input(2, 8, 64, 71)
+    assert_close(S.model_utils.get_graph_feature(d(xa), k=5), g["graph_feature"], 1e-5, "get_graph_feature")
+    pc = O.synth_clouds(2, 128, 72)[0].squeeze(-1)
+    torch.manual_seed(73)
+    fi = S.point_utils.farthest_point_sample(d(pc), 16)
+    assert fi.dtype == torch.int64 and np.array_equal(fi.cpu().numpy(), g["fps"])
+    ctr = S.point_utils.index_points(d(pc), fi)
+    assert_close(ctr, g["centres"], 1e-6, "index_points")
+    qb = S.point_utils.query_ball_point(0.3, 8, d(pc), ctr)
+    qk = S.point_utils.query_ball_point(None, 8, d(pc), ctr)
+    assert np.array_equal(qb.cpu().numpy(), g["ball"]) and np.array_equal(qk.cpu().numpy(), g["knn8"])
+    assert_close(S.point_utils.index_points(d(pc), qb), g["grouped"], 1e-6, "index_points grouped")
+    nodes_f = feat_input(2, 32, 16, 74)
+    assert_close(S.point_utils.upsample_inter(d(pc), ctr, None, d(nodes_f), 3), g["upsample"], 1e-4, "upsample_inter")
+    assert_close(S.point_utils.square_distance(d(pc), ctr), g["sqdist"], 1e-5, "square_distance")
+    fl = S.model_utils.focal_loss(num_classes=10, gamma=2, alpha=[0.05 * (i + 1) for i in range(10)], size_average=False)
+    rngf = np.random.Generator(np.random.PCG64(75))
+    lg = torch.from_numpy(rngf.standard_normal((12, 10)).astype(np.float32) * 2)
+    lb = torch.from_numpy(rngf.integers(0, 10, 12).astype(np.int64))
+    assert_close(fl(d(lg), d(lb)), g["focal1"], 1e-5, "focal loss")
+    assert_close(fl(d(lg) * 0.5, (d(lb) + 3) % 10), g["focal2"], 1e-5, "focal loss, second call (stateful alpha)")
+
+
 def test_mmd_modes_golden(S, golden):
     """The mmd_cal / weighting modes the SUG config does not exercise, against the unmodified reference:
     HARD_MMD, OFF, the unbiased estimator, weighting 'none' (mmd.py:25-41, 69-77, 178-202, 274-312)."""
