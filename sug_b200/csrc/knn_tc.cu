@@ -565,7 +565,8 @@ int knn_tc(const float* x, int B, int C, int N, int k, long long ld, int* idx, v
     a.dbg = dbg;
   }
   const int grid = min(num_sms(), B * a.mtiles_per_cloud);
-  ProfScope ps(KC_KNN_TC, 2.0 * 2.0 * B * (double)N * N * C, 4.0 * B * (double)N * (C + k), stream);
+  // algorithmic work (one distance matrix); the kernel computes it twice (two sweeps), which is its own business
+  ProfScope ps(KC_KNN_TC, 2.0 * B * (double)N * N * C, 4.0 * B * (double)N * (C + k), stream);
   if (k == 20) return knn_tc_launch<20>(tmX, a, grid, stream);
   return knn_tc_launch<40>(tmX, a, grid, stream);
 }
