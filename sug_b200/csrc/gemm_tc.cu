@@ -24,8 +24,9 @@ constexpr int TC_THREADS = 320;
 
 enum { EPI_STORE = 0, EPI_ATOMIC = 1 };
 
-// A_TS: the A operand (K-major) is staged in TMEM (hi and lo written by the split warps with
-// tcgen05.st), so shared memory only holds the raw A tile (TMA destination) and B hi / lo.  A 128x128x8
+// A_TS: the A operand is staged in TMEM (hi and lo written by the split warps with tcgen05.st; an
+// MN-major tile is transposed on the way: thread m gathers its 32 k-values from the swizzled tile), so
+// shared memory only holds the raw A tile (TMA destination) and B hi / lo.  A 128x128x8
 // tf32 MMA with both operands in shared memory reads 8 KB per 64 cycles = the whole 128 B/clk of an SM;
 // with three products per k-step the SS form is shared-memory-bandwidth bound, the TS form is not.
 template <int BN, bool A_TS>
@@ -58,7 +59,7 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, TcArgs p) {
-  constexpr bool A_TS = !A_MN;
+  constexpr bool A_TS = true;  // A always goes through TMEM (MN-major tiles are transposed on the way)
   using Cfg = TcCfg<BN, A_TS>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -137,7 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================================== MMA issuer =========================================
     {
-      constexpr uint32_t idesc = idesc_tf32(TBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = idesc_tf32(TBM, BN, (A_MN && !A_TS) ? 1 : 0, B_MN ? 1 : 0);  // TMEM A is K-major
       uint32_t it = 0, tile_it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
         const int ks = t / (p.tiles_n * p.tiles_m);
@@ -199,13 +200,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float4* b_hi = reinterpret_cast<const float4*>(sp + Cfg::A_SMEM);
         float4* b_lo = reinterpret_cast<float4*>(sp + Cfg::A_SMEM + Cfg::B_BYTES);
         if (A_TS) {
-          // this thread owns A row r (== TMEM lane): un-swizzle its 128 B, write hi and lo to TMEM
+          // this thread owns A row r (== TMEM lane): un-swizzle its 32 k-values, write hi and lo to TMEM
           const int r = (warp & 3) * 32 + lane;
           float hi[32], lo[32];
+          if (!A_MN) {  // K-major tile: the row is 128 contiguous (SWIZZLE_128B) bytes
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(sp + r * 128 + ((c ^ (r & 7)) << 4));
-            hi[4 * c] = v.x; hi[4 * c + 1] = v.y; hi[4 * c + 2] = v.z; hi[4 * c + 3] = v.w;
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = *reinterpret_cast<const float4*>(sp + r * 128 + ((c ^ (r & 7)) << 4));
+              hi[4 * c] = v.x; hi[4 * c + 1] = v.y; hi[4 * c + 2] = v.z; hi[4 * c + 3] = v.w;
+            }
+          } else {      // MN-major tile: four [32 k][32 m] blocks, 32 B chunks XOR-ed with (k % 4); lanes read
+                        // consecutive m of one k-row, i.e. conflict-free
+            const uint8_t* blk = sp + (r >> 5) * 4096;
+            const int ml = r & 31;
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk)
+              hi[kk] = *reinterpret_cast<const float*>(blk + kk * 128 + ((((ml >> 3) ^ (kk & 3)) << 5) | ((ml & 7) << 2)));
           }
 #pragma unroll
           for (int q = 0; q < 32; ++q) lo[q] = tf32_residual(hi[q]);
@@ -356,7 +366,7 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t r
 template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcArgs& args, int grid,
                      cudaStream_t stream) {
-  using Cfg = TcCfg<BN, !A_MN>;
+  using Cfg = TcCfg<BN, true>;
   static bool configured = false;
   if (!configured) {
     SUG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
