@@ -41,3 +41,4 @@ for k, v in a.items():
     rows.append((d / max(float(v.grad.norm()), 1e-4 * gmax), k))
 rows.sort(reverse=True)
 print(rows[:6])
+print("median", rows[len(rows) // 2][0], "of", len(rows), "parameters")
