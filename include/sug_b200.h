@@ -223,6 +223,17 @@ int sug_gemm_tc_f32(const float* a, int64_t lda, int a_mn_major, const float* b,
                     sug_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Class-weighted focal loss of the trainer (model_utils.py:131-176; gamma = 0 is the weighted cross entropy
+ * the SUG configs use):  L = reduce_r alpha_row[r] * ( -(1 - p_r)^gamma log p_r ),  p_r = softmax(preds_r)[labels_r],
+ * reduce = mean (mean != 0) or sum.  preds [R,C] row-major, labels int64 [R], alpha_row [R] (the per-row
+ * weights, i.e. the reference's alpha after its gather), loss: device scalar.  Backward: gout device scalar.
+ * ------------------------------------------------------------------------------------------- */
+int sug_focal_loss_fwd(const float* preds, const int64_t* labels, const float* alpha_row, int R, int C, float gamma,
+                       int mean, float* loss, sug_stream_t stream);
+int sug_focal_loss_bwd(const float* gout, const float* preds, const int64_t* labels, const float* alpha_row, int R,
+                       int C, float gamma, int mean, float* dpreds, sug_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimizer step of the trainer (train_dg_single_gpu.py:191-203, 329-335: three torch.optim.Adam).
  *   sug_adam_f32: one multi-tensor Adam update (L2 weight decay folded into the gradient, bias
  *                 corrected, torch's capturable arithmetic).  p/g/m/v_ptrs and sizes are DEVICE arrays

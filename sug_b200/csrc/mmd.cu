@@ -177,3 +177,83 @@ extern "C" int sug_chamfer_f32(const float* p1, const float* p2, int B, int N, i
   SUG_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- class-weighted focal loss (model_utils.py:131-176), one block --------------------------------------
+//   L = reduce_r  alpha_r * ( -(1 - p_r)^gamma * log p_r ),   p_r = softmax(preds_r)[label_r]
+// forward: scalar loss (sum or mean over the R rows); backward: d preds.
+namespace sug {
+
+__device__ __forceinline__ float focal_row(const float* __restrict__ z, int C, int y, float& lse) {
+  float m = -INFINITY;
+  for (int c = 0; c < C; ++c) m = fmaxf(m, z[c]);
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += expf(z[c] - m);
+  lse = m + logf(s);
+  return z[y] - lse;  // log p
+}
+
+__global__ void focal_fwd_kernel(const float* __restrict__ preds, const long long* __restrict__ labels,
+                                 const float* __restrict__ alpha_row, int R, int C, float gamma, int mean,
+                                 float* __restrict__ loss) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    float lse;
+    const float logp = focal_row(preds + (size_t)r * C, C, (int)labels[r], lse);
+    const float p = expf(logp);
+    const float w = gamma == 0.f ? 1.f : powf(1.f - p, gamma);
+    acc += (double)(alpha_row[r] * (-(w * logp)));
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = (float)(mean ? red[0] / R : red[0]);
+}
+
+__global__ void focal_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ preds,
+                                 const long long* __restrict__ labels, const float* __restrict__ alpha_row, int R, int C,
+                                 float gamma, int mean, float* __restrict__ dpreds) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float* z = preds + (size_t)r * C;
+  const int y = (int)labels[r];
+  float lse;
+  const float logp = focal_row(z, C, y, lse);
+  const float p = expf(logp);
+  // dL/dz_j = alpha * [ gamma (1-p)^(gamma-1) p log p - (1-p)^gamma ] * (delta_jy - s_j)
+  float coef;
+  if (gamma == 0.f) coef = -1.f;
+  else coef = gamma * powf(1.f - p, gamma - 1.f) * p * logp - powf(1.f - p, gamma);
+  coef *= alpha_row[r] * (*gout) * (mean ? 1.f / (float)R : 1.f);
+  for (int c = 0; c < C; ++c) {
+    const float s = expf(z[c] - lse);
+    dpreds[(size_t)r * C + c] = coef * ((c == y ? 1.f : 0.f) - s);
+  }
+}
+
+}  // namespace sug
+
+extern "C" int sug_focal_loss_fwd(const float* preds, const int64_t* labels, const float* alpha_row, int R, int C,
+                                  float gamma, int mean, float* loss, sug_stream_t stream) {
+  using namespace sug;
+  SUG_CHECK_ARG(preds && labels && alpha_row && loss && R > 0 && C > 0, "focal_loss_fwd: bad argument");
+  ProfScope ps(KC_MISC, 0, 0, (cudaStream_t)stream);
+  focal_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(preds, reinterpret_cast<const long long*>(labels), alpha_row, R, C,
+                                                       gamma, mean, loss);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_focal_loss_bwd(const float* gout, const float* preds, const int64_t* labels, const float* alpha_row,
+                                  int R, int C, float gamma, int mean, float* dpreds, sug_stream_t stream) {
+  using namespace sug;
+  SUG_CHECK_ARG(gout && preds && labels && alpha_row && dpreds && R > 0 && C > 0, "focal_loss_bwd: bad argument");
+  ProfScope ps(KC_MISC, 0, 0, (cudaStream_t)stream);
+  focal_bwd_kernel<<<cdiv(R, 128), 128, 0, (cudaStream_t)stream>>>(gout, preds, reinterpret_cast<const long long*>(labels),
+                                                                   alpha_row, R, C, gamma, mean, dpreds);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}

@@ -202,6 +202,11 @@ class focal_loss(nn.Module):
     def forward(self, preds, labels):
         preds = preds.view(-1, preds.size(-1))
         self.alpha = self.alpha.to(preds.device)
+        if preds.is_cuda:
+            # same arithmetic fused into one forward and one backward launch; the reference's statefulness
+            # (alpha re-gathered by the labels on every call, line 168) is kept
+            self.alpha = self.alpha.gather(0, labels.view(-1))
+            return ops.focal_loss(preds, labels.view(-1), self.alpha, float(self.gamma), bool(self.size_average))
         logsoft = F.log_softmax(preds, dim=1)
         soft = torch.exp(logsoft).gather(1, labels.view(-1, 1))
         logsoft = logsoft.gather(1, labels.view(-1, 1))

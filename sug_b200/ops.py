@@ -350,6 +350,42 @@ def linear(x, weight, bias=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# focal loss
+# ------------------------------------------------------------------------------------------------
+class _FocalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, preds, labels, alpha_row, gamma, mean):
+        preds = preds.float().contiguous()
+        R, C = preds.shape
+        loss = torch.empty((), dtype=torch.float32, device=preds.device)
+        lib = _lib.load()
+        with torch.cuda.device(preds.device):
+            _lib.check(lib.sug_focal_loss_fwd(_ptr(preds), _ptr(labels), _ptr(alpha_row), R, C, float(gamma), int(mean),
+                                              _ptr(loss), _stream()), "sug_focal_loss_fwd")
+        ctx.save_for_backward(preds, labels, alpha_row)
+        ctx.meta = (float(gamma), int(mean))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        preds, labels, alpha_row = ctx.saved_tensors
+        gamma, mean = ctx.meta
+        R, C = preds.shape
+        dp = torch.empty_like(preds)
+        lib = _lib.load()
+        with torch.cuda.device(preds.device):
+            _lib.check(lib.sug_focal_loss_bwd(_ptr(g.float().contiguous()), _ptr(preds), _ptr(labels), _ptr(alpha_row), R, C,
+                                              gamma, mean, _ptr(dp), _stream()), "sug_focal_loss_bwd")
+        return dp, None, None, None, None
+
+
+def focal_loss(preds, labels, alpha_row, gamma: float, mean: bool):
+    """model_utils.py:164-176 in one launch: preds [R,C], labels int64 [R], alpha_row [R] -> scalar."""
+    _need_cuda(preds, labels, alpha_row)
+    return _FocalFn.apply(preds, labels.long().contiguous(), alpha_row.float().contiguous(), gamma, mean)
+
+
+# ------------------------------------------------------------------------------------------------
 # MMD + Chamfer
 # ------------------------------------------------------------------------------------------------
 class _MmdFn(torch.autograd.Function):

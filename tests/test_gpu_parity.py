@@ -404,6 +404,18 @@ def test_api_functions_golden(S, golden):
     lb = torch.from_numpy(rngf.integers(0, 10, 12).astype(np.int64))
     assert_close(fl(d(lg), d(lb)), g["focal1"], 1e-5, "focal loss")
     assert_close(fl(d(lg) * 0.5, (d(lb) + 3) % 10), g["focal2"], 1e-5, "focal loss, second call (stateful alpha)")
+    # gradients of the fused kernel against the tensor-op spelling (the module's CPU branch), gamma = 2 and 0
+    for gamma, mean in ((2.0, False), (0.0, True), (0.5, True)):
+        a0 = [0.05 * (i + 1) for i in range(10)]
+        f_gpu = S.model_utils.focal_loss(num_classes=10, gamma=gamma, alpha=a0, size_average=mean)
+        f_cpu = S.model_utils.focal_loss(num_classes=10, gamma=gamma, alpha=a0, size_average=mean)
+        zc = lg.clone().requires_grad_(True)
+        zg = d(lg).requires_grad_(True)
+        lc, lgp = f_cpu(zc, lb), f_gpu(zg, d(lb))
+        (1.7 * lc).backward()
+        (1.7 * lgp).backward()
+        assert_close(lgp, lc, 1e-5, f"focal gamma={gamma}")
+        assert_close(zg.grad, zc.grad, 1e-4, f"focal grad gamma={gamma}")
 
 
 def test_mmd_modes_golden(S, golden):
