@@ -223,6 +223,21 @@ int sug_gemm_tc_f32(const float* a, int64_t lda, int a_mn_major, const float* b,
                     sug_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * SDA / MSA glue of model/mmd.py, each one launch:
+ *   sug_sda_sem_weights:   prob_weights_soft(..., weighting="mean2one") (mmd.py:134-148, 151-153, 198-201):
+ *                          softmax(pred) || onehot(label)*label_weight, batch-normalised, symmetric KL per row,
+ *                          scaled by int(1 / mean).  pred_* [m,10], label_* int64 [m] -> w [m].  No gradient
+ *                          (the reference detaches the predictions).
+ *   sug_soft_mmd_assemble: the operand of soft_mmd (mmd.py:56-66): z [2m, D+num_class] =
+ *                          [feat_s | onehot(label_s)*scale ; feat_t | onehot(label_t)*scale].
+ * ------------------------------------------------------------------------------------------- */
+int sug_sda_sem_weights(const float* pred_s, const float* pred_t, const int64_t* label_s, const int64_t* label_t, int m,
+                        int C, float label_weight, float* w, sug_stream_t stream);
+int sug_soft_mmd_assemble(const float* feat_s, int64_t lds, const float* feat_t, int64_t ldt, const int64_t* label_s,
+                          const int64_t* label_t, int m, int D, int num_class, float scale, float* z,
+                          sug_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Class-weighted focal loss of the trainer (model_utils.py:131-176; gamma = 0 is the weighted cross entropy
  * the SUG configs use):  L = reduce_r alpha_row[r] * ( -(1 - p_r)^gamma log p_r ),  p_r = softmax(preds_r)[labels_r],
  * reduce = mean (mean != 0) or sum.  preds [R,C] row-major, labels int64 [R], alpha_row [R] (the per-row

@@ -53,6 +53,8 @@ SIGNATURES = {
     "sug_node_offset_bwd": (I, [P, P, P, P, P, I, I, I, I, P, P]),
     "sug_interp_weight_fwd": (I, [P, P, P, I, I, I, I, P, P]),
     "sug_interp_weight_bwd": (I, [P, P, P, P, I, I, I, I, P, P]),
+    "sug_sda_sem_weights": (I, [P, P, P, P, I, I, F, P, P]),
+    "sug_soft_mmd_assemble": (I, [P, L, P, L, P, P, I, I, I, F, P, P]),
     "sug_focal_loss_fwd": (I, [P, P, P, I, I, F, I, P, P]),
     "sug_focal_loss_bwd": (I, [P, P, P, P, I, I, F, I, P, P]),
     "sug_adam_chunk": (I, []),

@@ -257,3 +257,109 @@ extern "C" int sug_focal_loss_bwd(const float* gout, const float* preds, const i
   SUG_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- SDA semantic sample weights (mmd.py:134-148 + 151-153 + 198-201), one block ---------------------------
+//   v = [softmax(pred) | onehot(label) * label_weight]          (per row, 2C entries)
+//   x = (v_s + 1e-8) / sum_all(v_s + 1e-8),  y likewise for the target batch
+//   dist_r = sum_c 0.5 (x log(x/y) - x + y) + 0.5 (y log(y/x) - y + x)
+//   "mean2one":  w_r = dist_r * int(1 / mean_r dist_r)          (integer truncation as in the reference)
+// and the assembly of the soft-MMD inputs  Z = [feat | onehot(label) * scale]  for both batches (mmd.py:56-66).
+namespace sug {
+
+__device__ __forceinline__ void softmax_row(const float* __restrict__ z, int C, float* __restrict__ out) {
+  float m = -INFINITY;
+  for (int c = 0; c < C; ++c) m = fmaxf(m, z[c]);
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) { out[c] = expf(z[c] - m); s += out[c]; }
+  for (int c = 0; c < C; ++c) out[c] = out[c] / s;
+}
+
+__device__ double block_sum256(double v, double* red) {
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double r = red[0];
+  __syncthreads();
+  return r;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+sda_sem_weights_kernel(const float* __restrict__ pred_s, const float* __restrict__ pred_t,
+                       const long long* __restrict__ label_s, const long long* __restrict__ label_t, int m,
+                       float label_weight, float* __restrict__ w) {
+  __shared__ double red[256];
+  const float eps = 1e-8f;
+  double ts = 0.0, tt = 0.0;
+  for (int r = threadIdx.x; r < m; r += 256) {
+    float ps[C], pt[C];
+    softmax_row(pred_s + (size_t)r * C, C, ps);
+    softmax_row(pred_t + (size_t)r * C, C, pt);
+    for (int c = 0; c < C; ++c) {
+      ts += (double)(ps[c] + eps) + (double)((c == (int)label_s[r] ? label_weight : 0.f) + eps);
+      tt += (double)(pt[c] + eps) + (double)((c == (int)label_t[r] ? label_weight : 0.f) + eps);
+    }
+  }
+  const float Ss = (float)block_sum256(ts, red), St = (float)block_sum256(tt, red);
+  double dsum = 0.0;
+  for (int r = threadIdx.x; r < m; r += 256) {
+    float ps[C], pt[C];
+    softmax_row(pred_s + (size_t)r * C, C, ps);
+    softmax_row(pred_t + (size_t)r * C, C, pt);
+    float d = 0.f;
+    for (int c = 0; c < 2 * C; ++c) {
+      const float vs = c < C ? ps[c] : ((c - C) == (int)label_s[r] ? label_weight : 0.f);
+      const float vt = c < C ? pt[c] : ((c - C) == (int)label_t[r] ? label_weight : 0.f);
+      const float x = (vs + eps) / Ss, y = (vt + eps) / St;
+      d += (x * logf(x / y) - x + y) * 0.5f + (y * logf(y / x) - y + x) * 0.5f;
+    }
+    w[r] = d;
+    dsum += (double)d;
+  }
+  const float mean = (float)(block_sum256(dsum, red) / m);
+  const float scale = (float)(int)(1.f / mean);
+  for (int r = threadIdx.x; r < m; r += 256) w[r] *= scale;
+}
+
+__global__ void soft_mmd_assemble_kernel(const float* __restrict__ fs, const float* __restrict__ ft, long long lds,
+                                         long long ldt, const long long* __restrict__ label_s,
+                                         const long long* __restrict__ label_t, int m, int D, int NC, float scale,
+                                         float* __restrict__ z) {
+  const int r = blockIdx.x;  // 0 .. 2m-1
+  const float* src = r < m ? fs + (size_t)r * lds : ft + (size_t)(r - m) * ldt;
+  const int lab = (int)(r < m ? label_s[r] : label_t[r - m]);
+  float* dst = z + (size_t)r * (D + NC);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) dst[c] = src[c];
+  for (int c = threadIdx.x; c < NC; c += blockDim.x) dst[D + c] = c == lab ? scale : 0.f;
+}
+
+}  // namespace sug
+
+extern "C" int sug_sda_sem_weights(const float* pred_s, const float* pred_t, const int64_t* label_s,
+                                   const int64_t* label_t, int m, int C, float label_weight, float* w, sug_stream_t stream) {
+  using namespace sug;
+  SUG_CHECK_ARG(pred_s && pred_t && label_s && label_t && w && m > 0, "sda_sem_weights: bad argument");
+  SUG_CHECK_ARG(C == 10, "sda_sem_weights: C=%d (the reference's one-hot has 10 classes, common_utils.py:161)", C);
+  ProfScope ps(KC_MISC, 0, 0, (cudaStream_t)stream);
+  sda_sem_weights_kernel<10><<<1, 256, 0, (cudaStream_t)stream>>>(pred_s, pred_t, reinterpret_cast<const long long*>(label_s),
+                                                                  reinterpret_cast<const long long*>(label_t), m, label_weight, w);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sug_soft_mmd_assemble(const float* feat_s, int64_t lds, const float* feat_t, int64_t ldt,
+                                     const int64_t* label_s, const int64_t* label_t, int m, int D, int num_class,
+                                     float scale, float* z, sug_stream_t stream) {
+  using namespace sug;
+  SUG_CHECK_ARG(feat_s && feat_t && label_s && label_t && z && m > 0 && D > 0 && num_class > 0, "soft_mmd_assemble: bad argument");
+  ProfScope ps(KC_MISC, 0, 8.0 * m * (2.0 * D + num_class), (cudaStream_t)stream);
+  soft_mmd_assemble_kernel<<<2 * m, 256, 0, (cudaStream_t)stream>>>(feat_s, feat_t, lds, ldt,
+                                                                   reinterpret_cast<const long long*>(label_s),
+                                                                   reinterpret_cast<const long long*>(label_t), m, D,
+                                                                   num_class, scale, z);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}

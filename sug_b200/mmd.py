@@ -50,6 +50,9 @@ def cal_sample_weights(data_s, data_t, args, label_s=None, label_t=None, KPC=Fal
 
 def soft_mmd(label_s, feat_s, label_t, feat_t, label_weight, sample_weights=None):
     """mmd.py:56-66: features || one-hot(label) * LABEL_SCALE, then the mixture-RBF MMD."""
+    if feat_s.is_cuda and feat_s.dim() == 2:  # operand assembled by one kernel instead of one-hot / scale / cat ops
+        return ops.soft_mmd(feat_s, feat_t, label_s.to(feat_s.device), label_t.to(feat_t.device), label_weight, sigma_list,
+                            sample_weights=sample_weights)
     oh_s = create_one_hot_labels(label_s).to(feat_s.device)
     oh_t = create_one_hot_labels(label_t).to(feat_t.device)
     fs = torch.cat((feat_s, oh_s * label_weight), dim=1)
@@ -102,6 +105,9 @@ def normalized(vec):
 def prob_weights_soft(pred_s, pred_t, label_s, label_t, label_weight, weighting="mean2one"):
     """mmd.py:134-148, on the device."""
     assert label_weight < 1, "For Entropy, Label weight should be less than one"
+    if weighting == "mean2one" and pred_s.is_cuda:  # the whole chain below in one launch
+        return ops.sda_sem_weights(pred_s, pred_t, label_s.to(pred_s.device), label_t.to(pred_t.device),
+                                   label_weight).reshape(1, -1)
     ps = torch.softmax(pred_s.detach().float(), dim=1).view(-1, 10)
     pt = torch.softmax(pred_t.detach().float(), dim=1).view(-1, 10)
     vs = torch.cat((ps, create_one_hot_labels(label_s).to(ps.device) * label_weight), dim=1)

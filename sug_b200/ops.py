@@ -388,42 +388,99 @@ def focal_loss(preds, labels, alpha_row, gamma: float, mean: bool):
 # ------------------------------------------------------------------------------------------------
 # MMD + Chamfer
 # ------------------------------------------------------------------------------------------------
+def _mmd_forward(ctx, z, m, weights, sigmas, biased):
+    """z [2m, D] (rows of X then Y) -> biased / unbiased mixture-RBF MMD^2; saves z and dL/dG for the backward."""
+    D = z.shape[1]
+    dev = z.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    coef = torch.empty(2 * m, 2 * m, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    ws = _workspace(lib.sug_mmd_ws_bytes(m, D), dev)
+    sg = (ctypes.c_float * len(sigmas))(*[float(s) for s in sigmas])
+    w = None
+    if weights is not None:
+        w = weights.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        if w.numel() != m:
+            raise RuntimeError(f"sample_weights has {w.numel()} entries, expected {m}")
+    with torch.cuda.device(dev):
+        _lib.check(lib.sug_mmd_rbf_fwd(_ptr(z), D, m, D, ctypes.cast(sg, ctypes.c_void_p), len(sigmas), _ptr(w),
+                                       int(biased), _ptr(loss), _ptr(coef), _ptr(ws), ws.numel(), _stream()),
+                   "sug_mmd_rbf_fwd")
+    ctx.save_for_backward(z, coef)
+    ctx.m = m
+    return loss
+
+
+def _mmd_backward(ctx, gloss):
+    z, coef = ctx.saved_tensors
+    m = ctx.m
+    D = z.shape[1]
+    dz = torch.empty_like(z)
+    g = gloss.detach().float().contiguous()
+    lib = _lib.load()
+    with torch.cuda.device(z.device):
+        _lib.check(lib.sug_mmd_rbf_bwd(_ptr(z), D, m, D, _ptr(coef), _ptr(g), _ptr(dz), D, _stream()),
+                   "sug_mmd_rbf_bwd")
+    return dz
+
+
 class _MmdFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, Y, weights, sigmas, biased):
-        m, D = X.shape
-        dev = X.device
         z = torch.cat((X.detach(), Y.detach()), 0).float().contiguous()
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        coef = torch.empty(2 * m, 2 * m, dtype=torch.float32, device=dev)
-        lib = _lib.load()
-        ws = _workspace(lib.sug_mmd_ws_bytes(m, D), dev)
-        sg = (ctypes.c_float * len(sigmas))(*[float(s) for s in sigmas])
-        w = None
-        if weights is not None:
-            w = weights.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
-            if w.numel() != m:
-                raise RuntimeError(f"sample_weights has {w.numel()} entries, expected {m}")
-        with torch.cuda.device(dev):
-            _lib.check(lib.sug_mmd_rbf_fwd(_ptr(z), D, m, D, ctypes.cast(sg, ctypes.c_void_p), len(sigmas), _ptr(w),
-                                           int(biased), _ptr(loss), _ptr(coef), _ptr(ws), ws.numel(), _stream()),
-                       "sug_mmd_rbf_fwd")
-        ctx.save_for_backward(z, coef)
-        ctx.m = m
-        return loss
+        return _mmd_forward(ctx, z, X.shape[0], weights, sigmas, biased)
 
     @staticmethod
     def backward(ctx, gloss):
-        z, coef = ctx.saved_tensors
-        m = ctx.m
-        D = z.shape[1]
-        dz = torch.empty_like(z)
-        g = gloss.detach().float().contiguous()
+        dz = _mmd_backward(ctx, gloss)
+        return dz[:ctx.m], dz[ctx.m:], None, None, None
+
+
+class _SoftMmdFn(torch.autograd.Function):
+    """soft_mmd (mmd.py:56-66): the operand [feat | onehot(label) * scale] is assembled by one kernel."""
+
+    @staticmethod
+    def forward(ctx, feat_s, feat_t, label_s, label_t, scale, weights, sigmas):
+        fs, ft = feat_s.detach().float(), feat_t.detach().float()
+        if fs.stride(1) != 1:
+            fs = fs.contiguous()
+        if ft.stride(1) != 1:
+            ft = ft.contiguous()
+        m, D = fs.shape
+        z = torch.empty(2 * m, D + 10, dtype=torch.float32, device=fs.device)
         lib = _lib.load()
-        with torch.cuda.device(z.device):
-            _lib.check(lib.sug_mmd_rbf_bwd(_ptr(z), D, m, D, _ptr(coef), _ptr(g), _ptr(dz), D, _stream()),
-                       "sug_mmd_rbf_bwd")
-        return dz[:m], dz[m:], None, None, None
+        with torch.cuda.device(fs.device):
+            _lib.check(lib.sug_soft_mmd_assemble(_ptr(fs), fs.stride(0), _ptr(ft), ft.stride(0), _ptr(label_s), _ptr(label_t),
+                                                 m, D, 10, float(scale), _ptr(z), _stream()), "sug_soft_mmd_assemble")
+        ctx.D = D
+        return _mmd_forward(ctx, z, m, weights, sigmas, True)
+
+    @staticmethod
+    def backward(ctx, gloss):
+        dz = _mmd_backward(ctx, gloss)
+        return dz[:ctx.m, :ctx.D], dz[ctx.m:, :ctx.D], None, None, None, None, None
+
+
+def soft_mmd(feat_s, feat_t, label_s, label_t, scale: float, sigma_list: Sequence[float], sample_weights=None):
+    _need_cuda(feat_s, feat_t, label_s, label_t)
+    if feat_s.shape != feat_t.shape:
+        raise AssertionError("X and Y must have the same shape")  # mmd.py:240
+    return _SoftMmdFn.apply(feat_s, feat_t, label_s.long().contiguous(), label_t.long().contiguous(), float(scale),
+                            sample_weights, tuple(sigma_list))
+
+
+def sda_sem_weights(pred_s, pred_t, label_s, label_t, label_weight: float):
+    """prob_weights_soft with weighting 'mean2one' (mmd.py:134-148) in one launch -> [m]."""
+    _need_cuda(pred_s, pred_t, label_s, label_t)
+    ps = pred_s.detach().float().reshape(-1, 10).contiguous()
+    pt = pred_t.detach().float().reshape(-1, 10).contiguous()
+    m = ps.shape[0]
+    w = torch.empty(m, dtype=torch.float32, device=ps.device)
+    lib = _lib.load()
+    with torch.cuda.device(ps.device):
+        _lib.check(lib.sug_sda_sem_weights(_ptr(ps), _ptr(pt), _ptr(label_s.long().contiguous()), _ptr(label_t.long().contiguous()),
+                                           m, 10, float(label_weight), _ptr(w), _stream()), "sug_sda_sem_weights")
+    return w
 
 
 def mix_rbf_mmd2(X, Y, sigma_list: Sequence[float], biased: bool = True, sample_weights=None):
