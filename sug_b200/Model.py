@@ -124,13 +124,27 @@ class DGCNN(nn.Module):
         B = x.size(0)
         k = self.k
         x0 = x_loc.transpose(1, 2).contiguous()  # point-major [B,N,3]
-        x1, x2 = self._trunk_fwd(x_loc, x0)
+        if self.share_trunk and self.training:
+            x1, x2 = self._trunk_fwd(x_loc, x0)
+            cat = None
+        else:
+            # x1, x2', x3, x4 are written straight into the channel slices of the concatenated tensor of
+            # Model.py:111 (no torch.cat copy; the backward hands out slices of its gradient)
+            cat = torch.empty(B, x0.shape[1], 512, dtype=torch.float32, device=x0.device)
+            x1 = self.conv1.edgeconv(x0, ops.knn_cm(x_loc, k), out=cat[:, :, 0:64])
+            x2 = self.conv2.edgeconv(x1, ops.knn_pm(x1, k))
         x_, node_pm, _ = self.node_fea_adapt.forward_pm(x2, x_loc)           # [B,N,128], [B,64 nodes,64]
         node_fea = node_pm.transpose(1, 2).unsqueeze(3)                       # reference layout [B,64,64,1]
-        x2 = ops.linear(x_, self.conv1d.weight, self.conv1d.bias)             # Conv1d(128,64,1) on point-major rows
-        x3 = self.conv3.edgeconv(x2, ops.knn_pm(x2, k))
-        x4 = self.conv4.edgeconv(x3, ops.knn_pm(x3, k))
-        feat = self._tail(torch.cat((x1, x2, x3, x4), dim=2))
+        if cat is None:
+            x2 = ops.linear(x_, self.conv1d.weight, self.conv1d.bias)         # Conv1d(128,64,1) on point-major rows
+            x3 = self.conv3.edgeconv(x2, ops.knn_pm(x2, k))
+            x4 = self.conv4.edgeconv(x3, ops.knn_pm(x3, k))
+            feat = self._tail(torch.cat((x1, x2, x3, x4), dim=2))
+        else:
+            x2 = ops.linear(x_, self.conv1d.weight, self.conv1d.bias, out=cat[:, :, 64:128])
+            x3 = self.conv3.edgeconv(x2, ops.knn_pm(x2, k), out=cat[:, :, 128:256])
+            x4 = self.conv4.edgeconv(x3, ops.knn_pm(x3, k), out=cat[:, :, 256:512])
+            feat = self._tail(ops.join_slices(cat, x1, x2, x3, x4))
         if node:
             return feat, node_fea, None
         return feat, node_fea

@@ -69,14 +69,14 @@ class conv_2d(nn.Module):
             return 0.0
         raise RuntimeError("fused paths need a ReLU / LeakyReLU block")
 
-    def edgeconv(self, x_pm, idx):
+    def edgeconv(self, x_pm, idx, out=None):
         """get_graph_feature(x, idx) -> self -> max over k, without the [B,2C,N,k] tensor.
-        x_pm [B,N,C], idx int32 [B,N,k] -> [B,N,Cout]  (Model.py:88-94)."""
+        x_pm [B,N,C], idx int32 [B,N,k] -> [B,N,Cout]  (Model.py:88-94); ``out``: see ops.edgeconv."""
         conv, bn = self.conv[0], self._bn_tick()
         if conv.bias is not None:
             raise RuntimeError("EdgeConv blocks are bias-free in the reference (Model.py:61-64)")
         return ops.edgeconv(x_pm, idx, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                            self.training, bn.eps, bn.momentum, self._slope())
+                            self.training, bn.eps, bn.momentum, self._slope(), out=out)
 
     def pool_max(self, x_pm):
         """self -> max over the N points (Model.py:272-274).  x_pm [B,N,Cin] -> [B,Cout]."""

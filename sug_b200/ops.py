@@ -106,7 +106,7 @@ def knn_reverse(idx: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 class _EdgeConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, idx, weight, gamma, beta, running_mean, running_var, training, eps, momentum, slope):
+    def forward(ctx, x, idx, weight, gamma, beta, running_mean, running_var, training, eps, momentum, slope, slot):
         x = _rows(x)
         B, N, C = x.shape
         Cout = weight.shape[0]
@@ -114,7 +114,7 @@ class _EdgeConvFn(torch.autograd.Function):
         dev = x.device
         w2 = weight.detach().reshape(Cout, 2 * C).contiguous()
         P = B * N
-        out = torch.empty(B, N, Cout, dtype=torch.float32, device=dev)
+        out = _take_slot(slot, (B, N, Cout), dev)
         ab = torch.empty(P, 2 * Cout, dtype=torch.float32, device=dev)
         lib = _lib.load()
         ws = _workspace(lib.sug_edgeconv_ws_bytes(B, N, C, Cout, k), dev)
@@ -128,7 +128,7 @@ class _EdgeConvFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.sug_edgeconv_fwd(_ptr(x), x.stride(1), _ptr(idx), _ptr(w2), _ptr(gamma.detach()),
                                             _ptr(beta.detach()), _ptr(running_mean), _ptr(running_var), B, N, C, Cout,
-                                            k, eps, momentum, slope, int(training), _ptr(out), Cout, _ptr(ab),
+                                            k, eps, momentum, slope, int(training), _ptr(out), out.stride(1), _ptr(ab),
                                             _ptr(ext), _ptr(arg), _ptr(ssum), _ptr(save), _ptr(ws), ws.numel(),
                                             _stream()), "sug_edgeconv_fwd")
         if training:
@@ -161,16 +161,60 @@ class _EdgeConvFn(torch.autograd.Function):
                                             _ptr(save), B, N, C, Cout, k, ctx.slope, _ptr(dx), C, 0, _ptr(dw),
                                             _ptr(dgamma), _ptr(dbeta), _ptr(dab), _ptr(ws), ws.numel(), _stream()),
                        "sug_edgeconv_bwd")
-        return dx, None, dw.view(ctx.wshape), dgamma, dbeta, None, None, None, None, None, None
+        return dx, None, dw.view(ctx.wshape), dgamma, dbeta, None, None, None, None, None, None, None
 
 
 def edgeconv(x, idx, weight, gamma, beta, running_mean, running_var, training: bool, eps: float = 1e-5,
-             momentum: float = 0.1, slope: float = 0.01):
+             momentum: float = 0.1, slope: float = 0.01, out=None):
     """Fused get_graph_feature -> 1x1 conv -> BatchNorm2d -> LeakyReLU -> max over k.
-    x [B,N,C] point-major, idx int32 [B,N,k], weight [Cout,2C,1,1] -> [B,N,Cout]."""
+    x [B,N,C] point-major, idx int32 [B,N,k], weight [Cout,2C,1,1] -> [B,N,Cout].
+    ``out``: optional [B,N,Cout] view (unit channel stride) of a wider buffer to write into, see ``join_slices``."""
     _need_cuda(x, idx, weight)
     return _EdgeConvFn.apply(x, idx, weight, gamma, beta, running_mean, running_var, bool(training), float(eps),
-                             float(momentum), float(slope))
+                             float(momentum), float(slope), None if out is None else [out])
+
+
+def _take_slot(slot, shape, dev):
+    """Output tensor of an op: a fresh one, or the caller's slice of a wider point-major buffer.  The slice is
+    handed over inside a list so that autograd does not see it as an input (the op's output is then an ordinary
+    output that happens to live in that buffer; nothing ever writes to it in place afterwards)."""
+    if slot is None:
+        return torch.empty(*shape, dtype=torch.float32, device=dev)
+    out = slot[0]
+    if (tuple(out.shape) != tuple(shape) or out.dtype != torch.float32 or out.stride(-1) != 1 or out.stride(-2) % 4 != 0
+            or out.data_ptr() % 16 != 0 or (out.dim() == 3 and out.stride(0) != out.shape[1] * out.stride(1))):
+        raise RuntimeError("output slot must be a float32 [B,N,C] slice with 16 B aligned rows of one uniform stride")
+    return out
+
+
+class _JoinSlicesFn(torch.autograd.Function):
+    """The concatenation of tensors that were WRITTEN into channel slices of one buffer: returns the buffer,
+    the backward hands every producer the matching slice of the gradient (views, no copies)."""
+
+    @staticmethod
+    def forward(ctx, holder, *parts):
+        ctx.widths = [p.shape[-1] for p in parts]
+        return holder[0].view(holder[0].shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, off = [], 0
+        for w in ctx.widths:
+            outs.append(g[..., off:off + w])
+            off += w
+        return (None, *outs)
+
+
+def join_slices(buf, *parts):
+    """``torch.cat(parts, dim=-1)`` for parts produced with ``out=buf[..., a:b]`` (consecutive slices of buf)."""
+    off = 0
+    for p in parts:
+        if p.data_ptr() != buf.data_ptr() + 4 * off or p.shape[:-1] != buf.shape[:-1]:
+            raise RuntimeError("join_slices: parts must be the consecutive channel slices of the buffer")
+        off += p.shape[-1]
+    if off != buf.shape[-1]:
+        raise RuntimeError("join_slices: the parts do not cover the buffer")
+    return _JoinSlicesFn.apply([buf], *parts)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -320,15 +364,20 @@ class _LinearFn(torch.autograd.Function):
     """x [.., K] -> x W^T + b  (fp32-accurate tensor-core GEMM)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, slot):
         K = x.shape[-1]
         x2 = x.reshape(-1, K)
         if x2.stride(1) != 1 or x2.dtype != torch.float32:
             x2 = x2.float().contiguous()
         w2 = weight.detach().reshape(weight.shape[0], K).contiguous()
-        y = _gemm_auto(x2, w2, None if bias is None else bias.detach())
         ctx.save_for_backward(x2, w2)
         ctx.meta = (tuple(x.shape), weight.shape, bias is not None)
+        if slot is not None:  # [B,N,Cout] slice of a wider buffer: rows of one uniform stride
+            out = _take_slot(slot, (*x.shape[:-1], w2.shape[0]), x.device)
+            rows = out.as_strided((x2.shape[0], w2.shape[0]), (out.stride(-2), 1))
+            _gemm_auto(x2, w2, None if bias is None else bias.detach(), out=rows)
+            return out
+        y = _gemm_auto(x2, w2, None if bias is None else bias.detach())
         return y.view(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
@@ -341,12 +390,12 @@ class _LinearFn(torch.autograd.Function):
         dx = _gemm_auto(g2, w2.t()).view(xshape) if ctx.needs_input_grad[0] else None
         dw = _gemm_auto(g2.t(), x2.t()).view(wshape) if ctx.needs_input_grad[1] else None
         db = g2.sum(0) if has_bias and ctx.needs_input_grad[2] else None
-        return dx, dw, db
+        return dx, dw, db, None
 
 
-def linear(x, weight, bias=None):
+def linear(x, weight, bias=None, out=None):
     _need_cuda(x, weight)
-    return _LinearFn.apply(x, weight, bias)
+    return _LinearFn.apply(x, weight, bias, None if out is None else [out])
 
 
 # ------------------------------------------------------------------------------------------------
