@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import importlib
 import runpy
+import os
 import sys
 import types
 
@@ -52,9 +53,28 @@ def _ensure(name: str, **attrs):
         return m
 
 
-def install():
+def install(fused_adam=None):
+    """Register the drop-in modules under the reference's import names.  ``fused_adam`` (default: env
+    ``SUG_B200_FUSED_ADAM=1``): additionally let the trainer's ``torch.optim.Adam(...)`` calls
+    (train_dg_single_gpu.py:191-203) build ``sug_b200.optim.FusedAdam`` for CUDA parameters -- same arithmetic,
+    one launch per param group; keyword arguments FusedAdam does not know fall back to torch's class."""
     from . import Model, mmd, model_pointnet, model_utils, ops, point_utils
     import torch
+
+    if fused_adam is None:
+        fused_adam = os.environ.get("SUG_B200_FUSED_ADAM", "0") == "1"
+    if fused_adam and not getattr(torch.optim.Adam, "_sug_wrapped", False):
+        from .optim import FusedAdam
+        _TorchAdam = torch.optim.Adam
+
+        def _adam(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, **kw):
+            params = list(params)
+            flat = [p for g in params for p in (g["params"] if isinstance(g, dict) else [g])]
+            if kw or not flat or not all(isinstance(p, torch.Tensor) and p.is_cuda for p in flat):
+                return _TorchAdam(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)
+            return FusedAdam(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        _adam._sug_wrapped = True
+        torch.optim.Adam = _adam
 
     class ChamferDistance(torch.nn.Module):
         """Call signature of the third-party package: (dist1, dist2, idx1, idx2); indices unused

@@ -793,6 +793,16 @@ def test_fused_adam_matches_torch(S):
         assert_close(b.detach(), a.detach(), 2e-6, f"fused adam param {k}")
     assert torch.equal(mine[5].detach(), ref[5].detach())
     assert float(o_mine.state[mine[0]]["step"]) == 6.0
+    # the opt-in switch of the compatibility layer hands CUDA parameters to FusedAdam
+    from sug_b200 import compat
+    real = torch.optim.Adam
+    try:
+        compat.install(fused_adam=True)
+        o = torch.optim.Adam([{"params": [mine[1]]}], lr=1e-3, weight_decay=5e-4)
+        assert isinstance(o, FusedAdam)
+        assert not isinstance(torch.optim.Adam([torch.nn.Parameter(torch.zeros(2))], lr=1e-3), FusedAdam)  # CPU tensor
+    finally:
+        torch.optim.Adam = real
 
 
 def test_graphed_step_matches_eager(S):
