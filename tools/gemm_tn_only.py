@@ -1,5 +1,7 @@
+"""Weight-gradient shaped GEMMs (dY^T X, both operands MN-major, K = B*N) on the tcgen05 path: time and error vs fp64.
+    python tools/gemm_tn_only.py"""
 import sys, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sug_b200 import ops
 dev = torch.device("cuda:0")
