@@ -115,7 +115,7 @@ class FusedAdam(torch.optim.Optimizer):
                     st[2] = torch.cuda.Event()
                     st[2].record(torch.cuda.current_stream(dev))
             plan.sig = sig
-            plan.keep = grads
+            plan.keep = [g for p, g in zip(ps, grads) if g is not p.grad]  # contiguous copies must outlive the launch
         return plan, ps
 
     # -- step -------------------------------------------------------------------------------------
