@@ -177,7 +177,9 @@ def edgeconv(x, idx, weight, gamma, beta, running_mean, running_var, training: b
 def _take_slot(slot, shape, dev):
     """Output tensor of an op: a fresh one, or the caller's slice of a wider point-major buffer.  The slice is
     handed over inside a list so that autograd does not see it as an input (the op's output is then an ordinary
-    output that happens to live in that buffer; nothing ever writes to it in place afterwards)."""
+    output that happens to live in that buffer).  The kernels write through raw pointers, so no autograd
+    version counter moves; a later torch in-place op on the buffer or on another slice would (correctly) make
+    autograd refuse the slices that were already returned -- the buffer must only be read afterwards."""
     if slot is None:
         return torch.empty(*shape, dtype=torch.float32, device=dev)
     out = slot[0]

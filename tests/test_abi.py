@@ -117,3 +117,33 @@ def test_shared_trunk_is_opt_in():
     assert os.environ.get("SUG_B200_SHARE_TRUNK", "0") != "1"
     net = Model.Net_MDA("DGCNN")
     assert net.g.share_trunk is False and net.g._trunk == {}
+
+
+def test_join_slices_autograd_contract():
+    """ops.join_slices: producers that wrote into consecutive channel slices of one buffer get the matching
+    slice of the gradient; anything else is refused.  (Pure autograd plumbing: runs on CPU tensors.)"""
+    from sug_b200 import ops
+    buf = torch.zeros(2, 5, 12)
+    a = torch.randn(2, 5, 4, requires_grad=True)
+    b = torch.randn(2, 5, 8, requires_grad=True)
+
+    class _Write(torch.autograd.Function):  # stands in for an op that writes its output into a slot
+        @staticmethod
+        def forward(ctx, x, slot):
+            slot[0].data.copy_(2 * x)  # like the CUDA kernels: a raw write, no autograd version bump
+            return slot[0]
+
+        @staticmethod
+        def backward(ctx, g):
+            return 2 * g, None
+
+    pa, pb = _Write.apply(a, [buf[:, :, 0:4]]), _Write.apply(b, [buf[:, :, 4:12]])
+    cat = ops.join_slices(buf, pa, pb)
+    assert cat.shape == buf.shape and cat.data_ptr() == buf.data_ptr()
+    w = torch.randn(2, 5, 12)
+    (cat * w).sum().backward()
+    assert torch.allclose(a.grad, 2 * w[:, :, 0:4]) and torch.allclose(b.grad, 2 * w[:, :, 4:12])
+    with pytest.raises(RuntimeError, match="consecutive"):
+        ops.join_slices(buf, pb, pa)
+    with pytest.raises(RuntimeError, match="cover"):
+        ops.join_slices(buf, pa)
