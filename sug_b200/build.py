@@ -2,10 +2,12 @@
 the library is plain CUDA runtime code behind the C ABI of include/sug_b200.h."""
 from __future__ import annotations
 
+import fcntl
 import hashlib
 import os
 import shutil
 import subprocess
+import tempfile
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -43,9 +45,26 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile every csrc/*.cu for sm_100a and link libsug_b200.so.  Returns its path."""
     stamp = os.path.join(OBJ, "stamp")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig
+    if not force and fresh():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
+    # one builder at a time (torchrun starts one process per GPU): the others wait on the lock and then find
+    # the finished library; the .so is linked under a temporary name and renamed, so a concurrent ctypes.CDLL
+    # never opens a half-written file
+    with open(os.path.join(OBJ, "lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():
+                return LIB
+            return _build_locked(dig, stamp, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(dig: str, stamp: str, verbose: bool) -> str:
     nvcc = _nvcc()
     logs = {}
 
@@ -59,9 +78,14 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
+    fd, tmp = tempfile.mkstemp(prefix="libsug_b200.", suffix=".so.tmp", dir=HERE)
+    os.close(fd)
+    r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
+        os.unlink(tmp)
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.chmod(tmp, 0o755)
+    os.replace(tmp, LIB)
     with open(os.path.join(OBJ, "ptxas.log"), "w") as fh:
         for s in sorted(logs):
             fh.write(f"==== {s}\n{logs[s]}\n")

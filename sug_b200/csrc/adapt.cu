@@ -337,11 +337,7 @@ extern "C" int sug_fps(const float* xyz, int B, int N, int npoint, const int32_t
   SUG_CHECK_ARG(B > 0 && N > 0 && npoint > 0, "fps: bad shape");
   size_t smem = sizeof(float) * 4 * (size_t)N;
   SUG_CHECK_ARG(smem <= 227 * 1024, "fps: N=%d needs %zu B of shared memory", N, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    SUG_CUDA(cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  SUG_TRY(ensure_dyn_smem((const void*)fps_kernel, smem));
   int nt = N >= 1024 ? 1024 : ((N + 31) / 32) * 32;
   ProfScope ps(KC_ADAPT, 0, 0, (cudaStream_t)stream);
   fps_kernel<<<B, nt, smem, (cudaStream_t)stream>>>(xyz, N, npoint, start, out_idx);
@@ -419,11 +415,7 @@ extern "C" int sug_knn_query(const float* xyz, const float* query, int B, int N,
   while (np2 < N) np2 <<= 1;
   size_t smem = 8 * (size_t)np2;
   SUG_CHECK_ARG(smem <= 227 * 1024, "knn_query: N=%d too large", N);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    SUG_CUDA(cudaFuncSetAttribute(knn_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  SUG_TRY(ensure_dyn_smem((const void*)knn_query_kernel, smem));
   int nt = np2 / 2 < 512 ? (np2 / 2 < 32 ? 32 : np2 / 2) : 512;
   ProfScope ps(KC_ADAPT, 0, 0, (cudaStream_t)stream);
   knn_query_kernel<<<dim3(S, B), nt, smem, (cudaStream_t)stream>>>(xyz, query, N, S, np2, nsample, out_idx);

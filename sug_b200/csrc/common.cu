@@ -1,7 +1,9 @@
 // Error reporting, device queries and the small BatchNorm-statistics kernels.
 #include <stdarg.h>
 
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -26,6 +28,21 @@ int num_sms() {
       n = 148;
   }
   return n;
+}
+
+int ensure_dyn_smem(const void* fn, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  int dev = 0;
+  SUG_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& have = done[std::make_pair(fn, dev)];
+  if (bytes > have) {
+    SUG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+  return 0;
 }
 
 // mean/invstd from fp64 sums; running stats follow nn.BatchNorm (momentum, unbiased variance).

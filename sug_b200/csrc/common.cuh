@@ -50,6 +50,9 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int num_sms();
+// Opt a kernel in to `bytes` of dynamic shared memory (cudaFuncAttributeMaxDynamicSharedMemorySize) on the
+// CURRENT device; remembered per (kernel, device), so a process that drives several GPUs configures each.
+int ensure_dyn_smem(const void* fn, size_t bytes);
 
 // ---- launch accounting / optional per-kernel-class CUDA-event timing (bench.py roofline) -------
 enum KClass {

@@ -478,10 +478,7 @@ static int smem_chunk(int B, int N, int Cout, int k) {
   if (Cout % 32 == 0 && smem_bytes_gather(N, 32, k) <= cap) return 32;
   return 0;
 }
-static int smem_attr(const void* fn, size_t bytes) {
-  if (bytes > 48 * 1024) SUG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return 0;
-}
+static int smem_attr(const void* fn, size_t bytes) { return ensure_dyn_smem(fn, bytes); }
 
 }  // namespace sug
 

@@ -367,12 +367,7 @@ template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcArgs& args, int grid,
                      cudaStream_t stream) {
   using Cfg = TcCfg<BN, true>;
-  static bool configured = false;
-  if (!configured) {
-    SUG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  SUG_TRY(ensure_dyn_smem((const void*)gemm_tc_kernel<BN, A_MN, B_MN>, Cfg::SMEM_BYTES));
   gemm_tc_kernel<BN, A_MN, B_MN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, args);
   SUG_LAUNCH_CHECK();
   return 0;

@@ -148,11 +148,7 @@ static size_t knn_simt_smem(int C, int k) {
 template <int K>
 static int knn_simt_launch(const float* x, int C, int N, int k, long long sb, long long sn, long long sc, int* idx,
                            dim3 grid, size_t smem, cudaStream_t stream) {
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    SUG_CUDA(cudaFuncSetAttribute(knn_simt_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  SUG_TRY(ensure_dyn_smem((const void*)knn_simt_kernel<K>, smem));
   knn_simt_kernel<K><<<grid, KTM, smem, stream>>>(x, C, N, k, sb, sn, sc, idx);
   SUG_LAUNCH_CHECK();
   return 0;
@@ -264,11 +260,7 @@ extern "C" int sug_knn_reverse(const int32_t* idx, int B, int N, int k, int32_t*
   SUG_CHECK_ARG(N < (1 << 23), "knn_reverse: N=%d too large for the packed edge format", N);
   size_t smem = sizeof(int) * (2 * (size_t)N + 1);
   SUG_CHECK_ARG(smem <= 227 * 1024, "knn_reverse: N=%d needs %zu B of shared memory", N, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    SUG_CUDA(cudaFuncSetAttribute(sug::knn_reverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  SUG_TRY(sug::ensure_dyn_smem((const void*)sug::knn_reverse_kernel, smem));
   sug::ProfScope ps(sug::KC_KNN_REV, 0, 4.0 * B * ((double)N * k * 2 + N + 1), (cudaStream_t)stream);
   sug::knn_reverse_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(idx, N, k, rev_ptr, rev_edge);
   SUG_LAUNCH_CHECK();

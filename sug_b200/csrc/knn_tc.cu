@@ -22,7 +22,6 @@
 // by two threads (one per group) which exchange T, list sizes and lists through shared memory.
 // Key = (-|x_i|^2 + 2 x_i.x_j) - |x_j|^2, the reference's operation order.
 #include <cfloat>
-#include <cstdlib>
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -57,7 +56,6 @@ struct KnnTcArgs {
   int* idx;         // [B,N,k]
   int B, N, C, k;
   int mtiles_per_cloud, ntiles;
-  int dbg;  // development: bit 0 = skip the selection work (times the TMA -> split -> MMA pipeline alone)
 };
 
 // ---- 32-input odd-even merge sort (Batcher), descending, on registers: 191 compare-exchanges ----
@@ -250,10 +248,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
               for (int j = 0; j < 4; ++j) {
                 const uint64_t dbh = dbh0 + 2 * j, dbl = dbl0 + 2 * j;
                 mma_tf32_ts(tacc, ta_lo + j * 8, dbh, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-                if (!(p.dbg & 4)) {
                 mma_tf32_ts(tacc, ta_hi + j * 8, dbl, idesc, 1u);
                 mma_tf32_ts(tacc, ta_hi + j * 8, dbh, idesc, 1u);
-                }
               }
               mma_commit(&empty[s]);
               if (kb == kbs - 1) mma_commit(&tfull[ab]);
@@ -295,12 +291,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
           mbar_wait(&full[s], (it / S) & 1);
           const float4* b_hi = reinterpret_cast<const float4*>(smem + (size_t)s * QSTAGE_BYTES);
           float4* b_lo = reinterpret_cast<float4*>(smem + (size_t)s * QSTAGE_BYTES + QTILE_BYTES);
-          if (!(p.dbg & 2)) {
 #pragma unroll
           for (int i = 0; i < QTILE_BYTES / 16 / 128; ++i) {
             const float4 w = b_hi[tix + i * 128];
             b_lo[tix + i * 128] = make_float4(tf32_residual(w.x), tf32_residual(w.y), tf32_residual(w.z), tf32_residual(w.w));
-          }
           }
           fence_proxy_async_smem();
           mbar_arrive(&ready[s]);
@@ -431,7 +425,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
         float va[16], vb[16];
         tmem_ld16(tsrc, va);
 #pragma unroll 1
-        for (int h = 0; h < ((p.dbg & 1) ? 0 : nh); h += 2) {
+        for (int h = 0; h < nh; h += 2) {
           tmem_ld_wait();
           if (h + 1 < nh) tmem_ld16(tsrc + (h + 1) * 16, vb);
           process(va, h, std::integral_constant<int, 0>{});
@@ -516,12 +510,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
 
 template <int K>
 static int knn_tc_launch(const CUtensorMap& tmX, const KnnTcArgs& a, int grid, cudaStream_t stream) {
-  static bool configured = false;
   const size_t smem = KnnSmem<K>::total;
-  if (!configured) {
-    SUG_CUDA(cudaFuncSetAttribute(knn_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  SUG_TRY(ensure_dyn_smem((const void*)knn_tc_kernel<K>, smem));
   knn_tc_kernel<K><<<grid, QTHREADS, smem, stream>>>(tmX, a);
   SUG_LAUNCH_CHECK();
   return 0;
@@ -551,19 +541,11 @@ int knn_tc(const float* x, int B, int C, int N, int k, long long ld, int* idx, v
   }
   SUG_LAUNCH_CHECK();
   CUtensorMap tmX;
-  static const int dbgv = getenv("SUG_KNN_DEBUG") ? atoi(getenv("SUG_KNN_DEBUG")) : 0;
-  if (dbgv & 8) SUG_TRY(make_tmap_2d(&tmX, x, (uint64_t)C, (uint64_t)P, (uint64_t)ld, 64, false, 64));   // timing experiment: 64 rows x 256 B
-  else if (dbgv & 16) SUG_TRY(make_tmap_2d(&tmX, x, (uint64_t)C, (uint64_t)P, (uint64_t)ld, 128, false, 32, 2));  // 256 B L2 promotion
-  else if (dbgv & 32) SUG_TRY(make_tmap_2d(&tmX, x, (uint64_t)C, (uint64_t)P, (uint64_t)ld, 128, false, 32, 0));  // no L2 promotion
-  else SUG_TRY(make_tmap_2d(&tmX, x, (uint64_t)C, (uint64_t)P, (uint64_t)ld, 128));
+  SUG_TRY(make_tmap_2d(&tmX, x, (uint64_t)C, (uint64_t)P, (uint64_t)ld, 128));
   KnnTcArgs a;
   a.xx = xx; a.idx = idx; a.B = B; a.N = N; a.C = C; a.k = k;
   a.mtiles_per_cloud = cdiv(N, 128);
   a.ntiles = cdiv(N, QBN);
-  {
-    static const int dbg = getenv("SUG_KNN_DEBUG") ? atoi(getenv("SUG_KNN_DEBUG")) : 0;
-    a.dbg = dbg;
-  }
   const int grid = min(num_sms(), B * a.mtiles_per_cloud);
   // algorithmic work (one distance matrix); the kernel computes it twice (two sweeps), which is its own business
   ProfScope ps(KC_KNN_TC, 2.0 * B * (double)N * N * C, 4.0 * B * (double)N * (C + k), stream);

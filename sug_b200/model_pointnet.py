@@ -1,6 +1,8 @@
-"""Drop-in for ``model_pointnet.DGCNN`` of the reference (model/model_pointnet.py:93-161): DGCNN
-without the node layer, any N, with the classifier head.  This is the model of BASELINE.json's
-config 1 (CPU-runnable case) and the only DGCNN usable at LiDAR scale (config 5)."""
+"""Drop-in for the reference's ``model/model_pointnet.py``: ``DGCNN`` (lines 93-161: DGCNN without the
+node layer, any N, with the classifier head -- the model of BASELINE.json's config 1 and the only DGCNN
+usable at LiDAR scale, config 5), ``Pointnet_cls`` (lines 5-55: the stand-alone PointNet classifier that
+``train_dg_single_gpu.py:8`` and ``dataset_splitter.py:6`` import) and ``Pointnet2_cls`` (lines 58-90:
+PointNet++, another model family -- out of scope; constructing it raises)."""
 from __future__ import annotations
 
 import torch
@@ -8,7 +10,53 @@ import torch.nn as nn
 
 from . import ops
 from .Model import K, Pointnet_c
-from .model_utils import conv_2d, transform_net
+from .model_utils import conv_2d, fc_layer, transform_net
+
+
+class Pointnet_cls(nn.Module):
+    """model_pointnet.py:5-55.  x [B,3,N,1] -> logits [B,num_class] (``adapt=True``: also the 1024-d feature)."""
+
+    def __init__(self, num_class=10):
+        super().__init__()
+        self.trans_net1 = transform_net(3, 3)
+        self.trans_net2 = transform_net(64, 64)
+        self.conv1 = conv_2d(3, 64, 1)
+        self.conv2 = conv_2d(64, 64, 1)
+        self.conv3 = conv_2d(64, 64, 1)
+        self.conv4 = conv_2d(64, 128, 1)
+        self.conv5 = conv_2d(128, 1024, 1)
+        self.mlp1 = fc_layer(1024, 512)
+        self.dropout1 = nn.Dropout2d(p=0.7)
+        self.mlp2 = fc_layer(512, 256)
+        self.dropout2 = nn.Dropout2d(p=0.7)
+        self.mlp3 = nn.Linear(256, num_class)
+
+    def forward(self, x, adapt=False):
+        transform = self.trans_net1(x)
+        x = torch.bmm(x.transpose(2, 1).squeeze(-1), transform).unsqueeze(3).transpose(2, 1)
+        x = self.conv2(self.conv1(x))
+        transform = self.trans_net2(x)
+        x = torch.bmm(x.transpose(2, 1).squeeze(-1), transform).unsqueeze(3).transpose(2, 1)
+        x = self.conv4(self.conv3(x))
+        x = self.conv5.pool_max(x.squeeze(3).transpose(1, 2))  # conv5 + BN + ReLU + max over N (lines 42-43), fused
+        mid_feature = x
+        x = self.dropout1(self.mlp1(x))
+        x = self.dropout2(self.mlp2(x))
+        x = ops.linear(x, self.mlp3.weight, self.mlp3.bias)
+        if adapt is False or adapt == False:  # noqa: E712  (the reference compares with ==)
+            return x
+        return x, mid_feature
+
+
+class Pointnet2_cls(nn.Module):
+    """model_pointnet.py:58-90 (PointNet++ set abstraction): a different model family, outside the accelerated
+    hot path.  The name exists so that ``from model.model_pointnet import *`` keeps
+    working; use the reference implementation for it."""
+
+    def __init__(self, num_class=10, normal_channel=False):
+        super().__init__()
+        raise NotImplementedError("Pointnet2_cls (PointNet++) is outside the accelerated hot path (SURVEY.md §2); "
+                                  "use the reference implementation for it")
 
 
 class DGCNN(nn.Module):

@@ -88,7 +88,9 @@ class FusedAdam(torch.optim.Optimizer):
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
         plan = self._plans.setdefault(gi, _GroupPlan())
         grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in ps]
-        sig = tuple((p.data_ptr(), g.data_ptr(), p.numel()) for p, g in zip(ps, grads))
+        # every pointer the device tables hold: a fresh .grad, or moments replaced by load_state_dict, rebuilds them
+        sig = tuple((p.data_ptr(), g.data_ptr(), self.state[p]["exp_avg"].data_ptr(), self.state[p]["exp_avg_sq"].data_ptr(),
+                     p.numel()) for p, g in zip(ps, grads))
         if sig != plan.sig:
             dev = ps[0].device if ps else None
             rows = [[p.data_ptr() for p in ps], [g.data_ptr() for g in grads],
@@ -117,6 +119,46 @@ class FusedAdam(torch.optim.Optimizer):
             plan.sig = sig
             plan.keep = [g for p, g in zip(ps, grads) if g is not p.grad]  # contiguous copies must outlive the launch
         return plan, ps
+
+    # -- (de)serialisation --------------------------------------------------------------------------
+    def _adopt_loaded_state(self):
+        """After ``load_state_dict`` / unpickling: the cached device tables point at the OLD moment buffers and the
+        group step counters know nothing of the loaded ``step`` values.  Drop the tables, restore one device step
+        scalar per group from the loaded state (torch.optim.Adam layout: a ``step`` per parameter) and re-alias every
+        ``state[p]['step']`` to it, so that bias correction continues where the checkpoint stopped and a later
+        ``state_dict()`` saves the live counter."""
+        self._plans = {}
+        self._gstate = {}
+        for gi, group in enumerate(self.param_groups):
+            steps = []
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st and "step" in st:
+                    steps.append(float(st["step"]))
+            if not steps:
+                continue
+            if max(steps) != min(steps):
+                raise RuntimeError("FusedAdam keeps one step counter per param group; the loaded state has parameters of "
+                                   f"group {gi} at different steps ({min(steps)} .. {max(steps)})")
+            dev = next(p.device for p in group["params"] if self.state.get(p))
+            gs = self._group_state(gi, group, dev)
+            gs["step"].fill_(steps[0])
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st:
+                    st["step"] = gs["step"]
+                    for k in ("exp_avg", "exp_avg_sq"):
+                        if not st[k].is_contiguous():
+                            st[k] = st[k].contiguous()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._adopt_loaded_state()
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._chunk = int(_lib.load().sug_adam_chunk())
+        self._adopt_loaded_state()
 
     # -- step -------------------------------------------------------------------------------------
     @torch.no_grad()

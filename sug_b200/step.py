@@ -107,7 +107,11 @@ class GraphedTrainStep:
         self.label = torch.zeros(batch, dtype=torch.long, device=dev)
         self.label_t = torch.zeros(batch, dtype=torch.long, device=dev)
         self.fps_dev = torch.zeros(4, batch, dtype=torch.int32, device=dev)
-        self.fps_host = torch.zeros(4, batch, dtype=torch.int32).pin_memory()
+        # pinned staging ring for the FPS start indices: a slot is rewritten only after the asynchronous upload
+        # that last read it has completed (its event), so the host can run ahead of the GPU by several steps
+        self.fps_host = [torch.zeros(4, batch, dtype=torch.int32).pin_memory() for _ in range(4)]
+        self.fps_event = [None] * len(self.fps_host)
+        self._fps_slot = 0
         self._call = 0
         self._alpha0 = criterion.alpha.detach().clone().to(dev) if hasattr(criterion, "alpha") else None
 
@@ -137,9 +141,17 @@ class GraphedTrainStep:
         return out
 
     def _draw_fps(self):
+        slot = self._fps_slot
+        self._fps_slot = (slot + 1) % len(self.fps_host)
+        if self.fps_event[slot] is not None:
+            self.fps_event[slot].synchronize()
+        host = self.fps_host[slot]
         for i in range(4):  # same CPU-RNG consumption as four eager forwards
-            self.fps_host[i] = torch.randint(0, self.N, (self.fps_host.shape[1],), dtype=torch.long).to(torch.int32)
-        self.fps_dev.copy_(self.fps_host, non_blocking=True)
+            host[i] = torch.randint(0, self.N, (host.shape[1],), dtype=torch.long).to(torch.int32)
+        self.fps_dev.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.fps_event[slot] = ev
 
     def warm(self, data, label, data_t, label_t, iters=3):
         """Eager warm-up on a side stream (required before capture; these passes DO train the model)."""

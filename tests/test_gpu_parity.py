@@ -805,6 +805,54 @@ def test_fused_adam_matches_torch(S):
         torch.optim.Adam = real
 
 
+def test_fused_adam_save_load_continue(S):
+    """FusedAdam must survive ``load_state_dict`` -- moments AND step counter restored, device tables
+    rebuilt -- and keep tracking torch.optim.Adam when training continues from the checkpoint."""
+    import copy
+    import io
+    from sug_b200.optim import FusedAdam
+    torch.manual_seed(11)
+    shapes = [(64, 6), (1000,), (33, 5)]
+    ref = [torch.randn(sh, device=DEV).requires_grad_(True) for sh in shapes]
+    mine = [p.detach().clone().requires_grad_(True) for p in ref]
+    mk_ref = lambda ps: torch.optim.Adam([{"params": ps[:2]}, {"params": ps[2:]}], lr=1e-2, weight_decay=5e-4)
+    mk_mine = lambda ps: FusedAdam([{"params": ps[:2]}, {"params": ps[2:]}], lr=1e-2, weight_decay=5e-4)
+    o_ref, o_mine = mk_ref(ref), mk_mine(mine)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+
+    def steps(o_a, ps_a, o_b, ps_b, n):
+        for _ in range(n):
+            for a, b in zip(ps_a, ps_b):
+                g = torch.randn(a.shape, device=DEV, generator=gen)
+                a.grad, b.grad = g.clone(), g.clone()
+            o_a.step()
+            o_b.step()
+    steps(o_ref, ref, o_mine, mine, 4)
+    buf = io.BytesIO()
+    torch.save(o_mine.state_dict(), buf)
+    buf.seek(0)
+    sd = torch.load(buf, map_location=DEV)
+    assert float(sd["state"][0]["step"]) == 4.0
+    # a NEW optimizer over NEW parameter tensors (a resumed process), and an in-place reload on the old one
+    mine2 = [p.detach().clone().requires_grad_(True) for p in mine]
+    o_new = mk_mine(mine2)
+    o_new.load_state_dict(sd)
+    o_mine.load_state_dict(copy.deepcopy(sd))
+    assert float(o_new.state[mine2[0]]["step"]) == 4.0
+    ref2 = [p.detach().clone().requires_grad_(True) for p in ref]
+    o_ref2 = mk_ref(ref2)
+    o_ref2.load_state_dict(copy.deepcopy(o_ref.state_dict()))
+    gen_state = gen.get_state()
+    steps(o_ref2, ref2, o_new, mine2, 3)
+    gen.set_state(gen_state)
+    steps(o_ref, ref, o_mine, mine, 3)
+    for k in range(len(shapes)):
+        assert_close(mine2[k].detach(), ref2[k].detach(), 2e-6, f"resumed (new optimizer) param {k}")
+        assert_close(mine[k].detach(), ref[k].detach(), 2e-6, f"resumed (in place) param {k}")
+    assert float(o_new.state[mine2[0]]["step"]) == 7.0
+    assert float(o_new.state_dict()["state"][2]["step"]) == 7.0   # a later state_dict() saves the live counter
+
+
 def test_graphed_step_matches_eager(S):
     """The CUDA-graph step (step.GraphedTrainStep) must train exactly like the eager step: same RNG
     consumption for FPS, same losses and weights after a few steps."""
