@@ -10,6 +10,7 @@
 //
 // This CUDA-core kernel is the production path for xyz inputs (C = 3).  Wider feature kNN uses
 // the same selection code behind the tcgen05 distance tiles (knn_tc.cu).
+#include <cfloat>
 #include <type_traits>
 
 #include "knn_select.cuh"
@@ -140,6 +141,198 @@ knn_simt_kernel(const float* __restrict__ x, int C, int N, int k, long long sb, 
   }
 }
 
+// ---- xyz clouds (C = 3): two-sweep selection on CUDA cores ---------------------------------------------
+// One thread owns one query point; the cloud's candidates are staged once per tile as (x, y, z, |x|^2) float4
+// and read as warp-wide broadcasts.  The distance costs 5 FMA-pipe operations, so -- like the tcgen05 kernel
+// (knn_tc.cu) -- the candidates are swept twice instead of maintaining a sorted list (whose ~100-instruction
+// inserts diverge across the lanes of a warp):
+//   sweep 0: 64 running slot maxima per thread (candidate j -> slot j mod 64): one FMNMX per
+//            candidate; the k-th largest slot maximum T is a lower bound of the row's k-th best key;
+//   sweep 1: keys are recomputed (bit-identical: same operations) and those >= T (~k + 10 per row) appended
+//            to a per-row list in shared memory with predicated stores -- no data-dependent control flow;
+//   final:   rank by counting, ties to the lower index; coalesced write of the [rows][k] block.
+// Key = (-|x_i|^2 + 2 x_i.x_j) - |x_j|^2 with sequential fp32 FMAs, the reference's order (model_utils.py:179-181).
+
+template <int K>
+struct XyzPlan {
+  static constexpr int NSLOT = 64;  // 64 slot maxima: ~k + 4 survivors expected for k = 20 (32 slots: k + 11, frequent prunes)
+  static constexpr int CAP = K <= 20 ? 56 : 80;  // k + one 16-candidate block + slack (see knn_prune)
+  // candidates per staged tile (a multiple of 64): 8 KB for k = 20, i.e. 50 KB per CTA with the lists = 4 CTAs
+  // per SM; the tile area is reused for CAP * 128 rank bytes at the end
+  static constexpr int XTILE = K <= 20 ? 512 : 640;
+  static constexpr size_t tile = 0;                                  // float4 [XTILE]
+  static constexpr size_t vals = tile + (size_t)XTILE * 16;          // [CAP][128] f32
+  static constexpr size_t ids = vals + (size_t)CAP * 128 * 4;        // [CAP][128] u16
+  static constexpr size_t total = ids + (size_t)CAP * 128 * 2;
+  static_assert((size_t)K * 128 * 4 <= (size_t)CAP * 128 * 4, "ranked block reuses the value lists");
+};
+
+template <int K>
+__global__ void __launch_bounds__(128, 4)
+knn_xyz_kernel(const float* __restrict__ x, int N, long long sb, long long sn, long long sc, int* __restrict__ idx_out) {
+  using L = XyzPlan<K>;
+  constexpr int CAP = L::CAP;
+  constexpr int NSLOT = L::NSLOT;
+  constexpr int XTILE = L::XTILE;
+  extern __shared__ __align__(16) uint8_t xsm[];
+  float4* tile = reinterpret_cast<float4*>(xsm + L::tile);
+  float* mv = reinterpret_cast<float*>(xsm + L::vals);
+  unsigned short* mi = reinterpret_cast<unsigned short*>(xsm + L::ids);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * 128;
+  const int row = row0 + tid;
+  const float* xb = x + (long long)b * sb;
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+  if (row < N) {
+    q0 = __ldg(xb + (long long)row * sn);
+    q1 = __ldg(xb + (long long)row * sn + sc);
+    q2 = __ldg(xb + (long long)row * sn + 2 * sc);
+  }
+  const float xxq = fmaf(q2, q2, fmaf(q1, q1, q0 * q0));
+  float gm[NSLOT];
+#pragma unroll
+  for (int q = 0; q < NSLOT; ++q) gm[q] = -INFINITY;
+  float T = -FLT_MAX;
+  int cnt = 0;
+
+  auto key_of = [&](const float4 c) {
+    const float dot = fmaf(q2, c.z, fmaf(q1, c.y, q0 * c.x));
+    return fmaf(2.f, dot, -xxq) - c.w;
+  };
+
+#pragma unroll 1
+  for (int sweep = 0; sweep < 2; ++sweep) {
+#pragma unroll 1
+    for (int t0 = 0; t0 < N; t0 += XTILE) {
+      __syncthreads();  // the previous tile is fully consumed
+      for (int e = tid; e < XTILE; e += 128) {
+        const int j = t0 + e;
+        float4 c = make_float4(0.f, 0.f, 0.f, INFINITY);  // out of range: key = -inf
+        if (j < N) {
+          c.x = __ldg(xb + (long long)j * sn);
+          c.y = __ldg(xb + (long long)j * sn + sc);
+          c.z = __ldg(xb + (long long)j * sn + 2 * sc);
+          c.w = fmaf(c.z, c.z, fmaf(c.y, c.y, c.x * c.x));
+        }
+        tile[e] = c;
+      }
+      __syncthreads();
+      const int nblk = (min(XTILE, N - t0) + NSLOT - 1) / NSLOT;  // whole NSLOT-blocks (padding reads as -inf)
+      if (sweep == 0) {
+#pragma unroll 1
+        for (int bk = 0; bk < nblk; ++bk) {
+#pragma unroll
+          for (int q = 0; q < NSLOT; ++q) gm[q] = fmaxf(gm[q], key_of(tile[bk * NSLOT + q]));
+        }
+      } else {
+        const int n16 = (min(XTILE, N - t0) + 15) >> 4;
+#pragma unroll 1
+        for (int hb = 0; hb < n16; ++hb) {
+          if (cnt > CAP - 16) knn_prune<K, CAP>(mv, mi, tid, cnt, T);
+          // predicated append: ~2 % of the candidates pass, so about half of the warp-wide store instructions have
+          // no active lane and cost no shared-memory wavefront
+          const uint32_t wv0 = (uint32_t)__cvta_generic_to_shared(mv + tid), wi0 = (uint32_t)__cvta_generic_to_shared(mi + tid);
+          uint32_t wv = wv0 + cnt * 512, wi = wi0 + cnt * 256;
+          const int base = t0 + hb * 16;
+          float v16[16];  // all keys first (independent loads and FMA chains), then the serial tail updates
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v16[q] = key_of(tile[hb * 16 + q]);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float v = v16[q];
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "setp.ge.f32 p, %2, %3;\n"
+                "@p st.shared.f32 [%0], %2;\n"
+                "@p st.shared.u16 [%1], %4;\n"
+                "@p add.s32 %0, %0, 512;\n"
+                "@p add.s32 %1, %1, 256;\n"
+                "}\n"
+                : "+r"(wv), "+r"(wi)
+                : "f"(v), "f"(T), "h"((unsigned short)(base + q))
+                : "memory");
+          }
+          cnt = (int)((wv - wv0) >> 9);
+        }
+      }
+    }
+    if (sweep == 0) {
+      // T = K-th largest slot maximum (every slot maximum is a distinct real candidate)
+      if constexpr (NSLOT == 32) {
+        oe_sort<0, 32>(gm);
+        T = fmaxf(gm[K - 1], -FLT_MAX);
+      } else {
+        float (&ga)[32] = *reinterpret_cast<float (*)[32]>(&gm[0]);
+        float (&gb)[32] = *reinterpret_cast<float (*)[32]>(&gm[32]);
+        oe_sort<0, 32>(ga);
+        oe_sort<0, 32>(gb);
+        float kth = -INFINITY;  // K-th largest of the union of two sorted lists: max_i min(a[i-1], b[K-i-1])
+#pragma unroll
+        for (int i = 0; i <= K; ++i) {
+          const int ia = i - 1, ib = K - i - 1;
+          if (ia >= 32 || ib >= 32) continue;
+          const float av = ia < 0 ? INFINITY : ga[ia];
+          const float bv = ib < 0 ? INFINITY : gb[ib];
+          kth = fmaxf(kth, fminf(av, bv));
+        }
+        T = fmaxf(kth, -FLT_MAX);
+      }
+    }
+  }
+
+  // ---- rank by counting: (value desc, position asc); positions are in candidate order -------------------
+  __syncthreads();  // all sweeps done: the candidate tile is free
+  // phase A: the rank of every list entry, as a byte, into the (now free) tile area
+  unsigned char* rkb = reinterpret_cast<unsigned char*>(xsm + L::tile);
+  static_assert((size_t)CAP * 128 <= (size_t)XTILE * 16, "rank bytes reuse the candidate tile");
+#pragma unroll 1
+  for (int i0 = 0; i0 < cnt; i0 += 4) {
+    float vi[4];
+    int rk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      vi[u] = (i0 + u < cnt) ? mv[(i0 + u) * 128 + tid] : INFINITY;
+      rk[u] = 0;
+    }
+    int j = 0;
+#pragma unroll 4
+    for (; j < i0; ++j) {  // earlier positions win ties
+      const float vj = mv[j * 128 + tid];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rk[u] += vj >= vi[u] ? 1 : 0;
+    }
+    for (; j < i0 + 4 && j < cnt; ++j) {
+      const float vj = mv[j * 128 + tid];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rk[u] += (vj > vi[u] || (vj == vi[u] && j < i0 + u)) ? 1 : 0;
+    }
+#pragma unroll 4
+    for (; j < cnt; ++j) {
+      const float vj = mv[j * 128 + tid];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rk[u] += vj > vi[u] ? 1 : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u < cnt) rkb[(i0 + u) * 128 + tid] = (unsigned char)min(rk[u], 255);
+  }
+  __syncthreads();  // every thread is done reading the value lists
+  int* rout = reinterpret_cast<int*>(xsm + L::vals);  // [K][128] ranked indices
+  for (int i = 0; i < cnt; ++i) {
+    const int rk = rkb[i * 128 + tid];
+    if (rk < K) rout[rk * 128 + tid] = (int)mi[i * 128 + tid];
+  }
+  __syncthreads();
+  const int rows = min(128, N - row0);
+  int* out = idx_out + ((long long)b * N + row0) * K;
+  for (int e = tid; e < rows * K; e += 128) {
+    const int r = e / K, s = e - r * K;
+    out[e] = rout[s * 128 + r];
+  }
+}
+
 static size_t knn_simt_smem(int C, int k) {
   const size_t sel = (k == 20 || k == 40) ? (size_t)(k > 32 ? k : 32) * KTM : TopK::smem_floats(k);
   return sizeof(float) * ((size_t)C * KQLD + KCC * KCLD + KTN + sel);
@@ -154,8 +347,22 @@ static int knn_simt_launch(const float* x, int C, int N, int k, long long sb, lo
   return 0;
 }
 
+template <int K>
+static int knn_xyz_launch(const float* x, int B, int N, long long sb, long long sn, long long sc, int* idx,
+                          cudaStream_t stream) {
+  const size_t smem = XyzPlan<K>::total;
+  SUG_TRY(ensure_dyn_smem((const void*)knn_xyz_kernel<K>, smem));
+  ProfScope ps(KC_KNN, 2.0 * B * (double)N * N * 3, 4.0 * B * (double)N * (3 + K), stream);
+  knn_xyz_kernel<K><<<dim3(cdiv(N, 128), B), 128, smem, stream>>>(x, N, sb, sn, sc, idx);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+
 int knn_simt(const float* x, int B, int C, int N, int k, long long sb, long long sn, long long sc, int* idx,
              cudaStream_t stream) {
+  if (C == 3 && N < 65536 && k == 20) return knn_xyz_launch<20>(x, B, N, sb, sn, sc, idx, stream);
+  // (k = 40 stays on the sorted-list kernel below: 64 slot maxima leave ~k + 22 survivors per row, which
+  //  overflows the lists too often; measured 920 us against 320 us)
   size_t smem = knn_simt_smem(C, k);
   SUG_CHECK_ARG(smem <= 227 * 1024, "knn: C=%d k=%d needs %zu B of shared memory (> 227 KB)", C, k, smem);
   dim3 grid(cdiv(N, KTM), B);

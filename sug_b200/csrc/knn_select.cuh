@@ -142,4 +142,64 @@ struct TopKReg {
   }
 };
 
+// ---- 32-input odd-even merge sort (Batcher), descending, on registers: 191 compare-exchanges ----
+__device__ __forceinline__ void cex(float& a, float& b) {
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  a = hi;
+  b = lo;
+}
+template <int LO, int N, int R>
+__device__ __forceinline__ void oe_merge(float (&a)[32]) {
+  constexpr int M = R * 2;
+  if constexpr (M < N) {
+    oe_merge<LO, N, M>(a);
+    oe_merge<LO + R, N, M>(a);
+#pragma unroll
+    for (int i = LO + R; i + R < LO + N; i += M) cex(a[i], a[i + R]);
+  } else {
+    cex(a[LO], a[LO + R]);
+  }
+}
+template <int LO, int N>
+__device__ __forceinline__ void oe_sort(float (&a)[32]) {
+  if constexpr (N > 1) {
+    oe_sort<LO, N / 2>(a);
+    oe_sort<LO + N / 2, N / 2>(a);
+    oe_merge<LO, N, 1>(a);
+  }
+}
+
+// Rare path: a (row, group) list is close to full.  Keep its k best (value desc, position asc),
+// compact, and raise the group's threshold to the k-th kept value.
+template <int K, int CAP>
+__device__ __noinline__ void knn_prune(float* mv, unsigned short* mi, int r, int& cnt, float& T) {
+  uint32_t keep0 = 0, keep1 = 0, keep2 = 0;
+  float newT = INFINITY;
+  for (int i = 0; i < cnt; ++i) {
+    const float vi = mv[i * 128 + r];
+    int rank = 0;
+    for (int j = 0; j < cnt; ++j) {
+      const float vj = mv[j * 128 + r];
+      rank += (vj > vi || (vj == vi && j < i)) ? 1 : 0;
+    }
+    if (rank < K) {
+      if (i < 32) keep0 |= 1u << i;
+      else if (i < 64) keep1 |= 1u << (i - 32);
+      else keep2 |= 1u << (i - 64);
+      newT = fminf(newT, vi);
+    }
+  }
+  int w = 0;
+  for (int i = 0; i < cnt; ++i) {
+    const uint32_t m = i < 32 ? keep0 : (i < 64 ? keep1 : keep2);
+    if ((m >> (i & 31)) & 1u) {
+      mv[w * 128 + r] = mv[i * 128 + r];
+      mi[w * 128 + r] = mi[i * 128 + r];
+      ++w;
+    }
+  }
+  cnt = w;
+  T = fmaxf(T, newT);
+}
+
 }  // namespace sug

@@ -29,9 +29,10 @@ def timeit(fn, iters=10):
 
 print("| op | N | k | C->Cout | B | time us | alg GB/s (% HBM) | alg TFLOP/s (% bf16) |")
 print("|---|---|---|---|---|---|---|---|")
-for N in (1024, 2048, 4096):
+QUICK = "--quick" in sys.argv  # step shapes only (B = 64, N = 1024, k = 20), no LiDAR-scale inference
+for N in ((1024,) if QUICK else (1024, 2048, 4096)):
     B = 65536 // N
-    for k in (20, 40):
+    for k in ((20,) if QUICK else (20, 40)):
         for C, Co in ((3, 64), (64, 64), (64, 128), (128, 256)):
             g = torch.Generator(device="cpu").manual_seed(N + k + C)
             if C == 3:
@@ -62,6 +63,8 @@ for N in (1024, 2048, 4096):
             by = B * N * (4.0 * (2 * Co + 2 * C) + 4.0 * k + Co)
             print(f"| edgeconv bwd | {N} | {k} | {C}->{Co} | {B} | {t2*1e6:.1f} | {by/t2/1e9:.0f} ({100*by/t2/1e9/peaks['hbm_gbs']:.1f}%) | {3*fl/t2/1e12:.1f} |")
 
+if QUICK:
+    sys.exit(0)
 # configs[4]: LiDAR-scale inference, N = 16384, k = 20 (the reference would need four 1.07 GB N x N tensors per cloud)
 net = model_pointnet.DGCNN().to(dev).eval()
 for B in (1, 4):
