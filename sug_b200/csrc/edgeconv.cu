@@ -341,21 +341,37 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
   const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + (tid % Q));
   // ---- stage the signed A chunk; deg-weighted sum of squares on the way ----
   double dsq[4] = {0, 0, 0, 0};
-  for (int e = tid; e < N * Q; e += 512) {  // 512 % Q == 0  =>  this thread's quad index is fixed
-    const int n = e / Q, qq = e - n * Q;
-    float4 v = __ldg(reinterpret_cast<const float4*>(ab + (cb + n) * ld + c0) + qq);
-    if (TRAIN) {
-      const float dg = (float)__ldg(deg + cb + n);
-      dsq[0] += (double)(dg * v.x * v.x);
-      dsq[1] += (double)(dg * v.y * v.y);
-      dsq[2] += (double)(dg * v.z * v.z);
-      dsq[3] += (double)(dg * v.w * v.w);
+  for (int e0 = tid; e0 < N * Q; e0 += 4 * 512) {  // 512 % Q == 0  =>  this thread's quad index is fixed
+    float4 vv[4];                                    // four independent loads in flight per thread
+    float dgs[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int e = e0 + w * 512;
+      const int n = e / Q, qq = e - n * Q;
+      if (e < N * Q) {
+        vv[w] = __ldg(reinterpret_cast<const float4*>(ab + (cb + n) * ld + c0) + qq);
+        if (TRAIN) dgs[w] = (float)__ldg(deg + cb + n);
+      }
     }
-    v.x = g4.x < 0.f ? -v.x : v.x;
-    v.y = g4.y < 0.f ? -v.y : v.y;
-    v.z = g4.z < 0.f ? -v.z : v.z;
-    v.w = g4.w < 0.f ? -v.w : v.w;
-    reinterpret_cast<float4*>(As + (size_t)n * CH)[qq] = v;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int e = e0 + w * 512;
+      if (e >= N * Q) break;
+      const int n = e / Q, qq = e - n * Q;
+      float4 v = vv[w];
+      if (TRAIN) {
+        const float dg = dgs[w];
+        dsq[0] += (double)(dg * v.x * v.x);
+        dsq[1] += (double)(dg * v.y * v.y);
+        dsq[2] += (double)(dg * v.z * v.z);
+        dsq[3] += (double)(dg * v.w * v.w);
+      }
+      v.x = g4.x < 0.f ? -v.x : v.x;
+      v.y = g4.y < 0.f ? -v.y : v.y;
+      v.z = g4.z < 0.f ? -v.z : v.z;
+      v.w = g4.w < 0.f ? -v.w : v.w;
+      reinterpret_cast<float4*>(As + (size_t)n * CH)[qq] = v;
+    }
   }
   // per-lane constants for the channels this lane owns in the gather phase
   const float4 gq = __ldg(reinterpret_cast<const float4*>(gamma + c0) + q);
@@ -457,6 +473,247 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
       atomicAdd(&sums[Cout + c0 + tid], s2);
     }
   }
+}
+
+// ---- backward, fast path -------------------------------------------------------------------------------
+// Two launches instead of (pre, main) over the transposed graph with 9 B of L2 gathers per edge and channel:
+//   route:  ghat = g act'(z);  G1, G2;  and the arg-routed term  Gs[j*_i[c], c] += ghat_i[c]  as ONE scatter
+//           of P*Cout values (red.global.add.f32 into the dA half of `dab`, zeroed before), instead of a masked
+//           gather of k*P*Cout (ghat, arg) pairs;
+//   main:   per (cloud, channel chunk) CTA the chunk's `b` rows are staged in shared memory once; T_j = sum of
+//           b over the reverse edges of j is gathered from there (the only per-edge work left: one LDS.128 and
+//           four adds per edge and four channels), a warp works on one destination row at a time with its
+//           32 / (CH/4) sub-groups taking different edges -- hub rows (in-degrees in the thousands in feature
+//           space) no longer serialise on one thread -- and rows are handed out dynamically.
+// The float atomics make the summation order of Gs (hence dA, dX, dW1) run-dependent at the ulp level, like
+// every scatter-add backward of the reference's own PyTorch path.
+__global__ void __launch_bounds__(256)
+edge_bwd_route_kernel(const float* __restrict__ gout, long long ldg, const float* __restrict__ ext,
+                      const uint8_t* __restrict__ arg, const int* __restrict__ idx, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const float* __restrict__ mean_invstd, long long P, int N, int k,
+                      int Cout, float slope, float* __restrict__ ghat, float* __restrict__ gs, long long ldgs,
+                      double* __restrict__ gsums) {
+  __shared__ double red[8][256];
+  constexpr int R = 2;  // rows in flight per thread (the arg -> idx -> atomic chain is two dependent loads deep); the
+                        // kernel is bound by the L2 atomic units (~140 G red/s measured), not by this
+  const int CQ = Cout >> 2;
+  const int PPB = 256 / CQ;  // rows per block step (CQ <= 256)
+  const int tid = threadIdx.x;
+  const int pl = tid / CQ, c4 = tid - pl * CQ;
+  const bool active = pl < PPB;
+  float mean[4], is[4], sc[4], sh[4];
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = 4 * c4 + u;
+      mean[u] = __ldg(mean_invstd + c);
+      is[u] = __ldg(mean_invstd + Cout + c);
+      sc[u] = __ldg(gamma + c) * is[u];
+      sh[u] = __ldg(beta + c) - mean[u] * sc[u];
+    }
+  }
+  float g1[4] = {0, 0, 0, 0}, g2[4] = {0, 0, 0, 0};   // fp32 over this thread's few rows, fp64 from there on
+  if (active) {
+    const long long stride = (long long)gridDim.x * PPB;
+    for (long long ib = (long long)blockIdx.x * PPB + pl; ib < P; ib += R * stride) {
+      float4 g[R], e[R];
+      uchar4 a[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const long long i = ib + r * stride;
+        if (i < P) {
+          g[r] = __ldg(reinterpret_cast<const float4*>(gout + i * ldg) + c4);
+          e[r] = __ldg(reinterpret_cast<const float4*>(ext + i * Cout) + c4);
+          a[r] = __ldg(reinterpret_cast<const uchar4*>(arg + i * Cout) + c4);
+        }
+      }
+      int jj[R][4];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const long long i = ib + r * stride;
+        if (i < P) {
+          const int* ip = idx + i * k;
+          jj[r][0] = __ldg(ip + a[r].x);
+          jj[r][1] = __ldg(ip + a[r].y);
+          jj[r][2] = __ldg(ip + a[r].z);
+          jj[r][3] = __ldg(ip + a[r].w);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const long long i = ib + r * stride;
+        if (i >= P) break;
+        const float gg[4] = {g[r].x, g[r].y, g[r].z, g[r].w};
+        const float ee[4] = {e[r].x, e[r].y, e[r].z, e[r].w};
+        float* grow = gs + (i / N) * N * ldgs + 4 * c4;
+        float gh[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float z = fmaf(sc[u], ee[u], sh[u]);
+          gh[u] = gg[u] * act_leaky_grad(z, slope);
+          g1[u] += gh[u];
+          g2[u] = fmaf(gh[u], (ee[u] - mean[u]) * is[u], g2[u]);
+          atomicAdd(grow + (long long)jj[r][u] * ldgs + u, gh[u]);
+        }
+        reinterpret_cast<float4*>(ghat + i * Cout)[c4] = make_float4(gh[0], gh[1], gh[2], gh[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    red[v][tid] = (double)g1[v];
+    red[4 + v][tid] = (double)g2[v];
+  }
+  __syncthreads();
+  if (active && pl == 0) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      double a = 0, q = 0;
+      for (int r = 0; r < PPB; ++r) {
+        a += red[v][r * CQ + c4];
+        q += red[4 + v][r * CQ + c4];
+      }
+      atomicAdd(&gsums[4 * c4 + v], a);
+      atomicAdd(&gsums[Cout + 4 * c4 + v], q);
+    }
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(512, 1)
+edge_bwd_main_smem_kernel(const float* __restrict__ ab, const float* __restrict__ ghat, const float* __restrict__ ssum,
+                          const int* __restrict__ rev_ptr, const int* __restrict__ rev_edge,
+                          const float* __restrict__ gamma, const float* __restrict__ mean_invstd,
+                          const double* __restrict__ gsums, long long P, int N, int k, int Cout,
+                          float* __restrict__ dab, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int Q = CH / 4;      // float4 lanes per row
+  constexpr int NSUB = 32 / Q;   // edge sub-groups of a warp == rows per batch
+  extern __shared__ __align__(16) float smem_f[];
+  float* Bs = smem_f;                                                         // [N][CH]
+  int* ptr_s = reinterpret_cast<int*>(smem_f + (size_t)N * CH);               // [N+1]  (padded to a multiple of 4)
+  unsigned short* src_s = reinterpret_cast<unsigned short*>(ptr_s + ((N + 4) & ~3));  // [N*k] source point of every reverse edge
+  __shared__ int next_row;
+  const int c0 = blockIdx.x * CH;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int q = lane % Q, sub = lane / Q;
+  const int ld = 2 * Cout;
+  const long long cb = (long long)b * N;
+  if (tid == 0) next_row = 0;
+  // the whole per-edge loop runs out of shared memory: b rows of the chunk, the cloud's CSR offsets and sources
+  // (eight independent loads in flight per thread: the staging is latency-, not bandwidth-bound)
+  for (int e0 = tid; e0 < N * Q; e0 += 8 * 512) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * 512;
+      const int n = e / Q, qq = e - n * Q;
+      if (e < N * Q) v[u] = __ldg(reinterpret_cast<const float4*>(ab + (cb + n) * ld + Cout + c0) + qq);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * 512;
+      const int n = e / Q, qq = e - n * Q;
+      if (e < N * Q) reinterpret_cast<float4*>(Bs + (size_t)n * CH)[qq] = v[u];
+    }
+  }
+  for (int e = tid; e <= N; e += 512) ptr_s[e] = __ldg(rev_ptr + (long long)b * (N + 1) + e);
+  {
+    const int* reb = rev_edge + cb * k;
+    const int E = N * k;
+    for (int e0 = tid; e0 < E; e0 += 8 * 512) {
+      int v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (e0 + u * 512 < E) ? __ldg(reb + e0 + u * 512) : 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (e0 + u * 512 < E) src_s[e0 + u * 512] = (unsigned short)(v[u] >> 8);
+    }
+  }
+  const double Md = (double)P * (double)k;
+  float mean[4], sc[4], c1[4], c2[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = c0 + 4 * q + u;
+    mean[u] = __ldg(mean_invstd + c);
+    const float is = __ldg(mean_invstd + Cout + c);
+    sc[u] = __ldg(gamma + c) * is;
+    const double G1 = gsums[c], G2 = gsums[Cout + c];
+    c1[u] = (float)(G1 / Md);
+    c2[u] = (float)(G2 / Md) * is;
+    if (b == 0 && tid < Q) {
+      dbeta[c] = (float)G1;
+      dgamma[c] = (float)G2;
+    }
+  }
+  __syncthreads();
+  const float kf = (float)k;
+  for (;;) {
+    int r0 = 0;
+    if (lane == 0) r0 = atomicAdd(&next_row, NSUB);
+    r0 = __shfl_sync(0xffffffffu, r0, 0);
+    if (r0 >= N) break;
+    // this lane finalises row r0 + sub: its operands are requested now and arrive while the batch is gathered
+    const int jl = r0 + sub;
+    const long long j = cb + min(jl, N - 1);
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(ab + j * ld + c0) + q);
+    const float4 gh = __ldg(reinterpret_cast<const float4*>(ghat + j * Cout + c0) + q);
+    const float4 S4 = __ldg(reinterpret_cast<const float4*>(ssum + j * Cout + c0) + q);
+    float4* dap = reinterpret_cast<float4*>(dab + j * ld + c0) + q;
+    const float4 G4 = *dap;  // the routed sums of the route kernel
+    float T[4] = {0.f, 0.f, 0.f, 0.f};  // sub-group s ends up with the row r0 + s
+    float degf = 0.f;
+#pragma unroll 1
+    for (int rr = 0; rr < NSUB; ++rr) {
+      const int jr = r0 + rr;
+      if (jr >= N) break;
+      const int lo = ptr_s[jr], hi = ptr_s[jr + 1];
+      float t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+      for (int t = lo + sub; t < hi; t += NSUB) {
+        const int i = src_s[t];
+        const float4 v = reinterpret_cast<const float4*>(Bs + (size_t)i * CH)[q];
+        t4[0] += v.x; t4[1] += v.y; t4[2] += v.z; t4[3] += v.w;
+      }
+#pragma unroll
+      for (int o = Q; o < 32; o <<= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t4[u] += __shfl_xor_sync(0xffffffffu, t4[u], o);
+      }
+      if (sub == rr) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) T[u] = t4[u];
+        degf = (float)(hi - lo);
+      }
+    }
+    if (jl < N) {
+      const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float gg[4] = {gh.x, gh.y, gh.z, gh.w};
+      const float SS[4] = {S4.x, S4.y, S4.z, S4.w};
+      const float Gs[4] = {G4.x, G4.y, G4.z, G4.w};
+      float dA[4], dB[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        dB[u] = sc[u] * (gg[u] - kf * c1[u] - c2[u] * (SS[u] - kf * mean[u]));
+        dA[u] = sc[u] * (Gs[u] - degf * c1[u] - c2[u] * (degf * (aa[u] - mean[u]) + T[u]));
+      }
+      *dap = make_float4(dA[0], dA[1], dA[2], dA[3]);
+      reinterpret_cast<float4*>(dab + j * ld + Cout + c0)[q] = make_float4(dB[0], dB[1], dB[2], dB[3]);
+    }
+  }
+}
+
+static size_t bwd_smem_bytes(int N, int CH, int k) {
+  return (size_t)N * CH * 4 + (size_t)((N + 4) & ~3) * 4 + (size_t)N * k * 2 + 16;
+}
+// chunk width of the shared-memory backward: the widest of 32 / 16 / 8 / 4 that divides Cout and whose staged
+// b rows fit; 0 = fall back to the global-memory kernels
+static int bwd_chunk(int N, int Cout, int k) {
+  const size_t cap = 220 * 1024;
+  if (N > 65535) return 0;  // 16-bit edge sources
+  for (int ch = 32; ch >= 4; ch >>= 1)
+    if (Cout % ch == 0 && bwd_smem_bytes(N, ch, k) <= cap) return ch;
+  return 0;
 }
 
 static int gather_grid(long long P, int Cout) {
@@ -591,7 +848,6 @@ extern "C" int sug_edgeconv_bwd(const float* gout, int64_t ldg, const float* x, 
                                 float slope, float* dx, int64_t lddx, int accumulate_dx, float* dw, float* dgamma,
                                 float* dbeta, float* dab, void* ws, size_t ws_bytes, sug_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  (void)idx;
   SUG_TRY(edge_check(B, N, C, Cout, k));
   SUG_CHECK_ARG(gout && x && rev_ptr && rev_edge && w && gamma && beta && ab && ext && arg && ssum &&
                     save_mean_invstd && dw && dgamma && dbeta && dab,
@@ -607,18 +863,48 @@ extern "C" int sug_edgeconv_bwd(const float* gout, int64_t ldg, const float* x, 
 
   SUG_CUDA(cudaMemsetAsync(gsums, 0, sizeof(double) * 2 * Cout, stream));
   const int grid = gather_grid(P, Cout);
-  {
-    ProfScope ps(KC_EDGE_BWD_PRE, 6.0 * P * Cout, 12.0 * P * Cout, stream);
-    edge_bwd_pre_kernel<<<grid, 256, 0, stream>>>(gout, ldg, ext, gamma, beta, save_mean_invstd, P, Cout, slope, ghat,
-                                                  gsums);
+  const int CHB = (Cout <= 1024 && idx != nullptr) ? bwd_chunk(N, Cout, k) : 0;
+  if (CHB != 0) {
+    // routed sums accumulate in the dA half of dab
+    SUG_CUDA(cudaMemset2DAsync(dab, sizeof(float) * 2 * Cout, 0, sizeof(float) * Cout, (size_t)P, stream));
+    {
+      ProfScope ps(KC_EDGE_BWD_PRE, 6.0 * P * Cout, (double)P * (17.0 * Cout + 4.0 * k), stream);
+      edge_bwd_route_kernel<<<grid, 256, 0, stream>>>(gout, ldg, ext, arg, idx, gamma, beta, save_mean_invstd, P, N, k,
+                                                      Cout, slope, ghat, dab, 2LL * Cout, gsums);
+    }
+    SUG_LAUNCH_CHECK();
+    {
+      ProfScope ps(KC_EDGE_BWD_MAIN, (double)P * k * Cout, (double)P * (28.0 * Cout + 4.0 * k), stream);
+      const size_t sm = bwd_smem_bytes(N, CHB, k);
+      const dim3 g2(Cout / CHB, B);
+#define SUG_BWD_MAIN(CH_)                                                                                          \
+  do {                                                                                                             \
+    SUG_TRY(smem_attr((const void*)edge_bwd_main_smem_kernel<CH_>, sm));                                           \
+    edge_bwd_main_smem_kernel<CH_><<<g2, 512, sm, stream>>>(ab, ghat, ssum, rev_ptr, rev_edge, gamma,              \
+                                                            save_mean_invstd, gsums, P, N, k, Cout, dab, dgamma,   \
+                                                            dbeta);                                                \
+  } while (0)
+      if (CHB == 32) SUG_BWD_MAIN(32);
+      else if (CHB == 16) SUG_BWD_MAIN(16);
+      else if (CHB == 8) SUG_BWD_MAIN(8);
+      else SUG_BWD_MAIN(4);
+#undef SUG_BWD_MAIN
+    }
+    SUG_LAUNCH_CHECK();
+  } else {
+    {
+      ProfScope ps(KC_EDGE_BWD_PRE, 6.0 * P * Cout, 12.0 * P * Cout, stream);
+      edge_bwd_pre_kernel<<<grid, 256, 0, stream>>>(gout, ldg, ext, gamma, beta, save_mean_invstd, P, Cout, slope, ghat,
+                                                    gsums);
+    }
+    SUG_LAUNCH_CHECK();
+    {
+      ProfScope ps(KC_EDGE_BWD_MAIN, 3.0 * P * k * Cout, (double)P * (8.0 * Cout + 9.0 * Cout + 4.0 * k + 8.0 * Cout), stream);
+      edge_bwd_main_kernel<<<grid, 256, 0, stream>>>(ab, ghat, arg, ssum, rev_ptr, rev_edge, gamma, save_mean_invstd,
+                                                     gsums, P, N, k, Cout, dab, dgamma, dbeta);
+    }
+    SUG_LAUNCH_CHECK();
   }
-  SUG_LAUNCH_CHECK();
-  {
-    ProfScope ps(KC_EDGE_BWD_MAIN, 3.0 * P * k * Cout, (double)P * (8.0 * Cout + 9.0 * Cout + 4.0 * k + 8.0 * Cout), stream);
-    edge_bwd_main_kernel<<<grid, 256, 0, stream>>>(ab, ghat, arg, ssum, rev_ptr, rev_edge, gamma, save_mean_invstd,
-                                                   gsums, P, N, k, Cout, dab, dgamma, dbeta);
-  }
-  SUG_LAUNCH_CHECK();
   // dWcat = dab^T x   ([2Cout, P] x [P, C])
   SUG_TRY(gemm_f32(dab, 1, 2 * Cout, x, 1, ldx, nullptr, dwcat, C, 2 * Cout, C, (int)P, 0, stream));
   {
