@@ -319,7 +319,14 @@ __global__ void knn_degree_kernel(const int* __restrict__ idx, long long E, int 
   }
 }
 
-template <int CH, bool TRAIN>
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// KB: bits of the arg-slot code embedded in the keys (0 = exact compare / select path)
+template <int CH, bool TRAIN, int KB>
 __global__ void __launch_bounds__(512, 1)
 edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ idx, const int* __restrict__ deg,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -330,7 +337,7 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
   constexpr int PPW = 32 / Q;    // points per warp step
   extern __shared__ __align__(16) float smem_f[];
   float* As = smem_f;                                        // [N][CH]
-  int* widx = reinterpret_cast<int*>(smem_f + (size_t)N * CH);  // [16 warps][PPW * k]
+  int* widx = reinterpret_cast<int*>(smem_f + (size_t)N * CH);  // [16 warps][2][PPW * k]
   __shared__ double red[16][Q][8];                           // stats partials per (warp, quad)
   const int c0 = blockIdx.x * CH;
   const int b = blockIdx.y;
@@ -389,14 +396,31 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
   }
   __syncthreads();
   double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
-  int* wi = widx + warp * (PPW * k);
+  // neighbour lists: PPW consecutive points => PPW*k consecutive ints, double buffered per warp -- the lists of the
+  // NEXT step are requested before the current step's gather and parked in shared memory after it, so their global
+  // latency is hidden behind ~20 neighbours of work
+  int* wbuf = widx + warp * (2 * PPW * k);
   const float kf = (float)k;
-  for (int p0 = warp * PPW; p0 < N; p0 += 16 * PPW) {
-    // stage this step's neighbour lists (PPW consecutive points => PPW*k consecutive ints)
-    const int cnt = min(PPW, N - p0) * k;
+  constexpr int NPF = (PPW * 64 + 31) / 32;  // prefetch registers per lane (k <= 64; larger k re-loads synchronously)
+  const bool can_pf = PPW * k <= NPF * 32;
+  {
+    const int p0 = warp * PPW;
+    if (p0 < N) {
+      const int cnt = min(PPW, N - p0) * k;
+      for (int e = lane; e < cnt; e += 32) wbuf[e] = __ldg(idx + (cb + p0) * k + e);
+    }
     __syncwarp();
-    for (int e = lane; e < cnt; e += 32) wi[e] = __ldg(idx + (cb + p0) * k + e);
-    __syncwarp();
+  }
+  int cur = 0;
+  for (int p0 = warp * PPW; p0 < N; p0 += 16 * PPW, cur ^= 1) {
+    int* wi = wbuf + cur * (PPW * k);
+    const int pn = p0 + 16 * PPW;
+    const int cntn = pn < N ? min(PPW, N - pn) * k : 0;
+    int pf[NPF];
+    if (can_pf) {
+#pragma unroll
+      for (int u = 0; u < NPF; ++u) pf[u] = (lane + 32 * u < cntn) ? __ldg(idx + (cb + pn) * k + lane + 32 * u) : 0;
+    }
     const int i = p0 + sub;
     if (i < N) {
       const float4 b4 = __ldg(reinterpret_cast<const float4*>(ab + (cb + i) * ld + Cout + c0) + q);
@@ -404,17 +428,65 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
       int bslot[4] = {0, 0, 0, 0};
       float s1[4] = {0, 0, 0, 0};
       const int* myi = wi + sub * k;
+      if (KB == 0) {
+        // exact arg: compare + two selects per neighbour and channel (any k <= 255)
 #pragma unroll 4
-      for (int s = 0; s < k; ++s) {
-        const int j = myi[s];
-        const float4 a4 = reinterpret_cast<const float4*>(As + (size_t)j * CH)[q];
-        const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+        for (int s = 0; s < k; ++s) {
+          const int j = myi[s];
+          const float4 a4 = reinterpret_cast<const float4*>(As + (size_t)j * CH)[q];
+          const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool gt = aa[u] > best[u];
-          best[u] = gt ? aa[u] : best[u];
-          bslot[u] = gt ? s : bslot[u];
-          if (TRAIN) s1[u] += aa[u];
+          for (int u = 0; u < 4; ++u) {
+            const bool gt = aa[u] > best[u];
+            best[u] = gt ? aa[u] : best[u];
+            bslot[u] = gt ? s : bslot[u];
+            if (TRAIN) s1[u] += aa[u];
+          }
+        }
+      } else {
+        // The ALU pipe bounds this loop (measured: 59 % ALU, 20 % FMA pipe).  Neighbours are taken in pairs: the exact
+        // maximum with one 3-input FMNMX3 per pair, and the arg slot from a second FMNMX3 over KEYS = the value with
+        // its KB lowest mantissa bits replaced by (2^KB - 1 - slot) -- one LOP3 per neighbour.  2 ALU operations per
+        // neighbour and channel instead of 3; `ext` stays the exact maximum, the recorded slot is the maximum's or
+        // that of a neighbour within 2^KB ulp of it (a near-tie: either choice routes the gradient legitimately).
+        constexpr unsigned KM = (1u << KB) - 1u;
+        float kbest[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int s = 0;
+#pragma unroll 2
+        for (; s + 1 < k; s += 2) {
+          const int j0 = myi[s], j1 = myi[s + 1];
+          const float4 a4 = reinterpret_cast<const float4*>(As + (size_t)j0 * CH)[q];
+          const float4 c4v = reinterpret_cast<const float4*>(As + (size_t)j1 * CH)[q];
+          const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float cc[4] = {c4v.x, c4v.y, c4v.z, c4v.w};
+          const unsigned code0 = KM - (unsigned)s, code1 = code0 - 1u;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            best[u] = fmax3(best[u], aa[u], cc[u]);
+            if (TRAIN) {
+              const float k0 = __uint_as_float((__float_as_uint(aa[u]) & ~KM) | code0);
+              const float k1 = __uint_as_float((__float_as_uint(cc[u]) & ~KM) | code1);
+              kbest[u] = fmax3(kbest[u], k0, k1);
+              s1[u] += aa[u] + cc[u];
+            }
+          }
+        }
+        if (s < k) {
+          const float4 a4 = reinterpret_cast<const float4*>(As + (size_t)myi[s] * CH)[q];
+          const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+          const unsigned code0 = KM - (unsigned)s;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            best[u] = fmaxf(best[u], aa[u]);
+            if (TRAIN) {
+              kbest[u] = fmaxf(kbest[u], __uint_as_float((__float_as_uint(aa[u]) & ~KM) | code0));
+              s1[u] += aa[u];
+            }
+          }
+        }
+        if (TRAIN) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) bslot[u] = (int)(KM - (__float_as_uint(kbest[u]) & KM));
         }
       }
       const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
@@ -442,6 +514,17 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
         o.w = act_leaky(fmaf(sc[3], e4[3], sh[3]), slope);
         *reinterpret_cast<float4*>(out + (cb + i) * ldo + c0 + 4 * q) = o;
       }
+    }
+    {
+      int* wn = wbuf + (cur ^ 1) * (PPW * k);
+      if (can_pf) {
+#pragma unroll
+        for (int u = 0; u < NPF; ++u)
+          if (lane + 32 * u < cntn) wn[lane + 32 * u] = pf[u];
+      } else {
+        for (int e = lane; e < cntn; e += 32) wn[e] = __ldg(idx + (cb + pn) * k + e);
+      }
+      __syncwarp();
     }
   }
   if (TRAIN) {
@@ -724,7 +807,7 @@ static int gather_grid(long long P, int Cout) {
 }
 
 static size_t smem_bytes_gather(int N, int CH, int k) {
-  return (size_t)N * CH * 4 + (size_t)16 * (128 / CH) * k * 4;
+  return (size_t)N * CH * 4 + (size_t)2 * 16 * (128 / CH) * k * 4;  // A chunk + double-buffered neighbour lists
 }
 // Channel-chunk width of the shared-memory gather: 32 when that still fills the GPU, 16 for narrow
 // layers, 0 (global-memory gather) when a cloud's chunk does not fit in shared memory.
@@ -792,15 +875,22 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
         SUG_CUDA(cudaMemsetAsync(deg, 0, sizeof(int) * P, stream));
         knn_degree_kernel<<<num_sms() * 4, 256, 0, stream>>>(idx, (long long)P * k, N, k, deg);
         const size_t sm = smem_bytes_gather(N, CH, k);
+#define SUG_GATHER_T(CH_, KB_)                                                                               \
+  do {                                                                                                       \
+    SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<CH_, true, KB_>, sm));                            \
+    edge_gather_smem_kernel<CH_, true, KB_><<<dim3(Cout / CH_, B), 512, sm, stream>>>(                       \
+        ab, idx, deg, gamma, beta, nullptr, N, k, Cout, slope, ext, arg, ssum, sums, nullptr, 0);            \
+  } while (0)
         if (CH == 32) {
-          SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<32, true>, sm));
-          edge_gather_smem_kernel<32, true><<<dim3(Cout / 32, B), 512, sm, stream>>>(
-              ab, idx, deg, gamma, beta, nullptr, N, k, Cout, slope, ext, arg, ssum, sums, nullptr, 0);
+          if (k <= 32) SUG_GATHER_T(32, 5);
+          else if (k <= 64) SUG_GATHER_T(32, 6);
+          else SUG_GATHER_T(32, 0);
         } else {
-          SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<16, true>, sm));
-          edge_gather_smem_kernel<16, true><<<dim3(Cout / 16, B), 512, sm, stream>>>(
-              ab, idx, deg, gamma, beta, nullptr, N, k, Cout, slope, ext, arg, ssum, sums, nullptr, 0);
+          if (k <= 32) SUG_GATHER_T(16, 5);
+          else if (k <= 64) SUG_GATHER_T(16, 6);
+          else SUG_GATHER_T(16, 0);
         }
+#undef SUG_GATHER_T
       } else {
         edge_gather_fwd_kernel<true><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, nullptr, (int)P, N, k, Cout, slope,
                                                                ext, arg, ssum, sums, nullptr, 0);
@@ -824,12 +914,12 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
       const int CH = smem_chunk(B, N, Cout, k);
       const size_t sm = CH ? smem_bytes_gather(N, CH, k) : 0;
       if (CH == 32) {
-        SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<32, false>, sm));
-        edge_gather_smem_kernel<32, false><<<dim3(Cout / 32, B), 512, sm, stream>>>(
+        SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<32, false, 5>, sm));
+        edge_gather_smem_kernel<32, false, 5><<<dim3(Cout / 32, B), 512, sm, stream>>>(
             ab, idx, nullptr, gamma, beta, mi_eval, N, k, Cout, slope, nullptr, nullptr, nullptr, nullptr, out, ldo);
       } else if (CH == 16) {
-        SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<16, false>, sm));
-        edge_gather_smem_kernel<16, false><<<dim3(Cout / 16, B), 512, sm, stream>>>(
+        SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<16, false, 5>, sm));
+        edge_gather_smem_kernel<16, false, 5><<<dim3(Cout / 16, B), 512, sm, stream>>>(
             ab, idx, nullptr, gamma, beta, mi_eval, N, k, Cout, slope, nullptr, nullptr, nullptr, nullptr, out, ldo);
       } else {
         edge_gather_fwd_kernel<false><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, mi_eval, (int)P, N, k, Cout, slope,
