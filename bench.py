@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="clouds per sub-domain per GPU")
     ap.add_argument("--mmd-scope", default="local", choices=["local", "global"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-reference", action="store_true",
+                    help="skip the torch_gpu_reference block (the reference algorithm as PyTorch ops on this GPU)")
     ap.add_argument("--profile-all", action="store_true", help="time every kernel class (diagnostics)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     ap.add_argument("--share-trunk", action="store_true",
@@ -110,49 +112,164 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
+def workload_config(B, world, mmd_scope="local", mode="cuda_graph", shared_trunk=False):
+    """The `config` object of BOTH arms (ours and --impl reference): BASELINE.json configs[1] / [2]."""
+    return {"workload": "SUG DG train step: Net_MDA(DGCNN, k=20) x4 forwards + backward + 3 Adam, "
+                        "CE(2 heads x 2 sub-domains) + GEO/SEM soft-MMD with SDA weights "
+                        "(DG_unified_loss_onedataset_shapenet.yaml) = BASELINE.json configs[1]",
+            "clouds_per_step_per_gpu": 2 * B, "batch_per_subdomain": B, "points": N_POINTS, "k": 20,
+            "classes": 10, "parallelism": f"dp{world}", "mmd_scope": mmd_scope, "execution": mode,
+            "shared_trunk": bool(shared_trunk),
+            "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle port) on the host cores, bounded sample
 # ---------------------------------------------------------------------------------------------------
-def cpu_step_time(batch: int, steps: int, warmup: int):
-    """Seconds per SUG step of the CPU oracle at `batch`+`batch` clouds (all host threads)."""
-    from oracle import sug_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = O.clone_state(O.synth_state("Net_MDA:DGCNN"), requires_grad=True)
-    params = [v for v in sd.values() if v.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=5e-4)
-    data, label = O.synth_clouds(batch, N_POINTS, 0)
-    data_t, label_t = O.synth_clouds(batch, N_POINTS, 1)
-    label, label_t = label % batch if batch < 10 else label, label_t
-    crit = O.FocalLoss([0.1] * 10, 0.0)
-    ts = []
-    for it in range(warmup + steps):
-        crit.alpha = torch.full((10,), 0.1)  # keep the reference's re-gathered alpha valid for small batches
+class CpuStep:
+    """One SUG step of the CPU oracle (oracle/sug_oracle.py: the reference's algorithm in functional PyTorch, pinned to
+    the unmodified reference by tests/golden) at `batch` + `batch` clouds on all host threads."""
+
+    def __init__(self, batch: int):
+        from oracle import sug_oracle as O
+        self.O = O
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.batch = batch
+        self.sd = O.clone_state(O.synth_state("Net_MDA:DGCNN"), requires_grad=True)
+        self.opt = torch.optim.Adam([v for v in self.sd.values() if v.requires_grad], lr=1e-4, weight_decay=5e-4)
+        self.data, label = O.synth_clouds(batch, N_POINTS, 0)
+        self.data_t, self.label_t = O.synth_clouds(batch, N_POINTS, 1)
+        self.label = label % batch if batch < 10 else label
+        self.crit = O.FocalLoss([0.1] * 10, 0.0)
+        self.threads = torch.get_num_threads()
+
+    def __call__(self):
+        self.crit.alpha = torch.full((10,), 0.1)  # keep the reference's re-gathered alpha valid for small batches
         t0 = time.perf_counter()
-        out = O.sug_losses(sd, data, label, data_t, label_t, crit)
+        out = self.O.sug_losses(self.sd, self.data, self.label, self.data_t, self.label_t, self.crit)
         out["loss"].backward()
-        opt.step()
-        opt.zero_grad()
+        self.opt.step()
+        self.opt.zero_grad()
         float(out["loss"].detach())
-        if it >= warmup:
-            ts.append(time.perf_counter() - t0)
-    return sum(ts) / len(ts), torch.get_num_threads()
+        return time.perf_counter() - t0
+
+
+def host_mem_gib():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 16.0
+
+
+def pick_cpu_batch(total_steps: int, budget_s: float):
+    """Largest per-sub-domain batch in {64, 32, 16, 8, 4} whose `total_steps` steps fit the time budget and whose
+    activations (~0.45 GiB per cloud pair: the reference materialises every [B,2C,N,k] edge tensor) fit the host."""
+    probe = CpuStep(4)
+    probe()
+    per_cloud = min(probe(), probe()) / 8.0
+    del probe
+    mem = host_mem_gib()
+    for bs in (64, 32, 16, 8, 4):
+        if total_steps * per_cloud * 2 * bs <= budget_s and 0.5 * bs + 6.0 <= mem:
+            return bs, per_cloud
+    return 4, per_cloud
 
 
 def run_reference(args, rank, emit):
+    """--impl reference: the reference's own CPU path (there is no compiled reference: it is Python / PyTorch, and
+    /root/reference does not travel to the GPU box, so the arm times the oracle port), all host threads, EXACTLY
+    `--warmup` untimed and `--steps` timed steps of the GPU arm's workload.  Each step is a bounded sample: the
+    same SUG step at the largest batch that keeps the whole run within ~3 minutes (stated in cpu_baseline.sample);
+    clouds/s = clouds of the sample / its time."""
     if rank != 0:
         return
-    bs = 4
-    sec, cores = cpu_step_time(bs, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    bs, _ = pick_cpu_batch(args.steps + args.warmup, 170.0)
+    step = CpuStep(bs)
+    for _ in range(args.warmup):
+        step()
+    ts = [step() for _ in range(args.steps)]
+    sec = sum(ts) / len(ts)
     val = 2 * bs / sec
+    cfg = workload_config(B_PER_GPU, 1, mode="cpu_eager")
+    cfg["parallelism"] = "cpu"
+    cfg["sample_batch_per_subdomain"] = bs
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SUG DG train step (DGCNN + MSA MMD + SDA), CPU port of the reference algorithm",
-                       "clouds_per_step": 2 * bs, "points": N_POINTS, "k": 20},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"SUG step at {bs}+{bs} clouds x {N_POINTS} pts (batch reduced from 64+64), "
-                                       f"oracle/sug_oracle.py on {cores} host threads"},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": step.threads, "kind": "port",
+                             "sample": f"{args.steps} timed + {args.warmup} warm-up SUG steps at {bs}+{bs} clouds x {N_POINTS} pts "
+                                       f"(a bounded sample of the 64+64 step: same network, losses, backward, Adam), "
+                                       f"oracle/sug_oracle.py on {step.threads} host threads; best step {2 * bs / min(ts):.1f} clouds/s"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+
+
+def torch_gpu_reference(dev, B, steps=3):
+    """The reference ALGORITHM on this GPU: the oracle's plain PyTorch ops (torch.topk on the materialised N x N
+    matrix, the [B,2C,N,k] edge tensor, cuDNN / cuBLAS convolutions, Python FPS loop with its host syncs) moved to the
+    device -- the kernels the reference's own modules would launch.  This is the denominator of north_star's
+    ">= 3x the reference's PyTorch-CUDA path"; timed with cuDNN TF32 on (PyTorch's default, what the reference gets)
+    and off (fp32, the accuracy this library delivers).  Checker code (oracle/), never on the product path."""
+    from oracle import sug_oracle as O
+    sd = {k: v.to(dev) for k, v in O.clone_state(O.synth_state("Net_MDA:DGCNN")).items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and v.dim() > 0 and "running_" not in k:
+            v.requires_grad_(True)
+    opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-4, weight_decay=5e-4)
+    data, label = (t.to(dev) for t in O.synth_clouds(B, N_POINTS, 0))
+    data_t, label_t = (t.to(dev) for t in O.synth_clouds(B, N_POINTS, 1))
+    crit = O.FocalLoss([0.1] * 10, 0.0)
+    out = {}
+    saved = torch.backends.cudnn.allow_tf32
+    try:
+        for name, tf32 in (("tf32_default", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            ts = []
+            for it in range(steps + 1):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                o = O.sug_losses(sd, data, label, data_t, label_t, crit)
+                o["loss"].backward()
+                opt.step()
+                opt.zero_grad()
+                float(o["loss"].detach())
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 1:
+                    ts.append(e0.elapsed_time(e1))
+            ms = sum(ts) / len(ts)
+            out[name] = {"ms_per_step": ms, "clouds_per_s": 2 * B / ms * 1e3}
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved
+    out["peak_mem_gib"] = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    out["what"] = (f"oracle/sug_oracle.py (the reference's algorithm as plain PyTorch ops) on cuda, {B}+{B} clouds, "
+                   f"1 warm-up + {steps} timed steps per mode, CUDA events")
+    return out
+
+
+def measure_tf32_peak(dev):
+    """Dense TF32 matmul throughput of this GPU the way MEASURED_PEAKS.json measures bf16 (torch.matmul 8192^3, best
+    of 10): the tensor-pipe denominator of the fp32-accurate kernels (3xTF32 => a third of it)."""
+    n = 8192
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    saved = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        best = 1e9
+        for it in range(12):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                best = min(best, e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = saved
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -316,6 +433,17 @@ def _main(args, rank, emit):
     e2e_value = clouds_per_step * args.steps / (ms_e2e / 1e3)
 
     trace("done timing")
+    # ---- data parallel: every replica must hold the same weights after the timed steps ---------------------
+    replicas_in_sync = None
+    if world > 1:
+        with torch.no_grad():
+            cs = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+            cs2 = torch.stack([p.detach().double().abs().sum() for p in model.parameters()]).sum().reshape(1)
+            v = torch.cat([cs, cs2])
+            lo, hi = v.clone(), v.clone()
+            tdist.all_reduce(lo, op=tdist.ReduceOp.MIN)
+            tdist.all_reduce(hi, op=tdist.ReduceOp.MAX)
+            replicas_in_sync = bool(torch.equal(lo, hi))
     if rank != 0:
         if world > 1:
             tdist.destroy_process_group()
@@ -323,50 +451,96 @@ def _main(args, rank, emit):
 
     # ---- roofline of the dominant kernel class --------------------------------------------------------
     pk = peaks()
+    tf32_peak = measure_tf32_peak(dev)
     d = prof[dom]
     if graphed is not None:
         # graph replays re-record the same event pairs: the totals are those of the LAST timed step
         d = dict(d, launches=d["timed"], flops=d["flops"], bytes=d["bytes"])
     per_launch_s = (d["ms"] / 1e3) / max(1, d["timed"])
-    # a GEMM-class kernel is judged against whichever roofline binds it harder at the measured peaks
+    GEMM_LIKE = ("gemm_simt", "gemm_tc", "knn_simt", "knn_tc")
+
+    def judge(name, flops_pl, bytes_pl, sec):
+        """A GEMM-class kernel is judged against whichever roofline binds it harder at the measured peaks."""
+        t_tensor = flops_pl / (pk["tensor"] * 1e12) if name in GEMM_LIKE else 0.0
+        t_hbm = bytes_pl / (pk["hbm"] * 1e9)
+        tfl, gbs = flops_pl / sec / 1e12, bytes_pl / sec / 1e9
+        if t_tensor > t_hbm:
+            r = {"bound": "tensor", "achieved": tfl, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tfl / pk["tensor"]}
+        else:
+            r = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}
+        r.update({"tflops": tfl, "gbps": gbs})
+        if name in GEMM_LIKE:
+            # all tensor-core kernels here are fp32-accurate 3xTF32: three TF32 products per algorithmic one
+            r["frac_of_3xtf32_ceiling"] = tfl / (tf32_peak / 3.0)
+        return r
     flops_pl, bytes_pl = d["flops"] / max(1, d["launches"]), d["bytes"] / max(1, d["launches"])
-    t_tensor = flops_pl / (pk["tensor"] * 1e12) if dom in ("gemm_simt", "gemm_tc", "knn_simt", "knn_tc") else 0.0
-    t_hbm = bytes_pl / (pk["hbm"] * 1e9)
-    tensor_bound = t_tensor > t_hbm
-    if tensor_bound:
-        ach = flops_pl / per_launch_s / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-                "traffic": None}
-    else:
-        ach = bytes_pl / per_launch_s / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": None}
-    roof["tflops"] = flops_pl / per_launch_s / 1e12
-    roof["gbps"] = bytes_pl / per_launch_s / 1e9
+    roof = judge(dom, flops_pl, bytes_pl, per_launch_s)
+    tensor_bound = roof["bound"] == "tensor"
+    # DRAM traffic of the class's representative launch from the committed ncu --set full capture (profiles/)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp)).get(dom)
+        if t:
+            traffic = t["dram_bytes_per_launch"]
+            roof["traffic_capture"] = {k: t[k] for k in t if k != "dram_bytes_per_launch"}
+    roof["traffic"] = traffic
     roof.update({"kernel": dom, "launches_timed": int(d["timed"]), "avg_launch_us": per_launch_s * 1e6,
-                 "share_of_step": d["ms"] / (ms / args.steps if graphed is not None else ms), "peak_source": pk["src"] + (" bf16 sustained" if tensor_bound else " copy")})
+                 "algorithmic_bytes_per_launch": bytes_pl, "algorithmic_flops_per_launch": flops_pl,
+                 "share_of_step": d["ms"] / (ms / args.steps if graphed is not None else ms),
+                 "peak_source": pk["src"] + (" bf16 sustained" if tensor_bound else " copy")})
+
+    # every kernel class of the step (the metric names the kNN / EdgeConv kernels, which are not the largest class):
+    # launches, average device time and algorithmic work per launch from the instrumented eager step that precedes
+    # the timed region (same kernels, same shapes; the per-class minimum of two steps)
+    by_class = {}
+    for name, v in prof1.items():
+        if not v["launches"] or not v["timed"] or v["ms"] <= 0:
+            continue
+        sec = v["ms"] / 1e3 / v["timed"]
+        r = judge(name, v["flops"] / v["launches"], v["bytes"] / v["launches"], sec)
+        r.update({"launches_per_step": int(v["launches"]), "avg_launch_us": sec * 1e6, "ms_per_step": v["ms"]})
+        by_class[name] = {k: (round(x, 4) if isinstance(x, float) else x) for k, x in r.items()}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SUG DG train step: Net_MDA(DGCNN, k=20) x4 forwards + backward + 3 Adam, "
-                                   "CE(2 heads x 2 sub-domains) + GEO/SEM soft-MMD with SDA weights "
-                                   "(DG_unified_loss_onedataset_shapenet.yaml)",
-                       "clouds_per_step_per_gpu": 2 * B, "batch_per_subdomain": B, "points": N_POINTS, "k": 20,
-                       "classes": 10, "parallelism": f"dp{world}", "mmd_scope": args.mmd_scope, "execution": mode,
-                       "shared_trunk": bool(args.share_trunk),
-                       "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed"},
+            "config": workload_config(B, world, args.mmd_scope, mode, args.share_trunk),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "roofline": roof, "kernel_ms_one_step": breakdown}
+            "gpu_launches": launches, "roofline": roof, "roofline_by_class": by_class,
+            "peaks": {"hbm_gbs": pk["hbm"], "bf16_tflops_sustained": pk["tensor"], "bf16_tflops_burst": pk["tensor_burst"],
+                      "source": pk["src"], "tf32_tflops_measured_here": tf32_peak,
+                      "tf32_how": "torch.matmul fp32 8192^3 with allow_tf32, best of 10, CUDA events (same method as "
+                                  "MEASURED_PEAKS.json's bf16 burst figure)"},
+            "kernel_ms_one_step": breakdown}
+    if replicas_in_sync is not None:
+        line["replicas_in_sync"] = replicas_in_sync
+
+    if world == 1 and not args.no_torch_reference:
+        # free this arm's graph pools first: the reference algorithm keeps ~50 GB of activations at 64+64
+        del graphed
+        run_step = None
+        torch.cuda.empty_cache()
+        try:
+            ref = torch_gpu_reference(dev, B)
+            ref["speedup_of_this_library"] = {"vs_tf32_default": ref["tf32_default"]["ms_per_step"] / (ms / args.steps),
+                                              "vs_fp32": ref["fp32"]["ms_per_step"] / (ms / args.steps)}
+            line["torch_gpu_reference"] = ref
+        except Exception as e:  # never lose the measured line over the comparison arm
+            line["torch_gpu_reference"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     if not args.no_cpu_baseline:
-        bs = 4
-        sec, cores = cpu_step_time(bs, 1, 0)
-        line["cpu_baseline"] = {"value": 2 * bs / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"1 SUG step at {bs}+{bs} clouds x {N_POINTS} pts (batch reduced from 64+64), "
-                                          f"oracle/sug_oracle.py on {cores} host threads"}
+        # the reference's CPU path on this box's host cores: BASELINE.json configs[0]-sized sample of the same step
+        # (32+32 clouds when the host has the memory), one warm-up step, best of two
+        bs = 32 if host_mem_gib() >= 24.0 else (16 if host_mem_gib() >= 14.0 else 8)
+        step_cpu = CpuStep(bs)
+        step_cpu()
+        sec = min(step_cpu(), step_cpu())
+        line["cpu_baseline"] = {"value": 2 * bs / sec, "unit": UNIT, "cores": step_cpu.threads, "kind": "port",
+                                "sample": f"SUG step at {bs}+{bs} clouds x {N_POINTS} pts (sample of the 64+64 step), "
+                                          f"1 warm-up + best of 2, oracle/sug_oracle.py on {step_cpu.threads} host threads"}
     emit(line)
     if world > 1:
         tdist.destroy_process_group()

@@ -55,6 +55,15 @@ def pairwise_neg_sqdist(x: torch.Tensor) -> torch.Tensor:
     return -xx - inner - xx.transpose(2, 1)
 
 
+def knn_row_hash(idx):
+    """16-bit hash of every row's neighbour SET (order-independent): idx [B,N,k] integer -> int32 [B,N] in
+    [0, 65536).  Used to compare neighbour graphs at sizes where storing the lists is impractical."""
+    s = idx.long().sort(dim=-1)[0]
+    w = torch.arange(1, 2 * s.shape[-1], 2, device=s.device, dtype=torch.long)
+    h = (s * w).sum(-1) * 40503 + (s * s).sum(-1) * 2654435761
+    return ((h ^ (h >> 16)) & 0xFFFF).to(torch.int32)
+
+
 KNN_TRACE = None  # set to a list to record every neighbour list knn() returns (teacher forcing in tests)
 
 

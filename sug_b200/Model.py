@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .model_utils import adapt_layer_off, conv_2d, exact_conv, fc_layer, transform_net
+from .model_utils import adapt_layer_off, conv_2d, fc_layer, transform_net
 
 K = 20  # Model.py:52
 
@@ -32,18 +32,14 @@ class CALayer(nn.Module):
         self.bn = nn.BatchNorm1d(4096)
 
     def forward(self, x):
-        if x.is_cuda:
-            # the two 1x1 convolutions on a [B,C,1,1] tensor are plain linear layers; cuBLAS fp32
-            # instead of cuDNN's (TF32-by-default, slow weight-gradient) convolution kernels
-            c0, c2 = self.conv_du[0], self.conv_du[2]
-            v = x.reshape(x.shape[0], -1)
-            y = F.relu(F.linear(v, c0.weight.view(c0.out_channels, -1), c0.bias))
-            y = torch.sigmoid(F.linear(y, c2.weight.view(c2.out_channels, -1), c2.bias))
-            return self.bn(v * y + v)
-        y = self.conv_du(x)
-        y = x * y + x
-        y = y.view(y.shape[0], -1)
-        return self.bn(y)
+        # the two 1x1 convolutions on a [B,C,1,1] tensor are plain linear layers: the library's fp32-accurate GEMM
+        # (no cuDNN / cuBLAS kernel on the path, no CPU branch); the gate and the BatchNorm1d stay in ATen
+        ops._need_cuda(x)
+        c0, c2 = self.conv_du[0], self.conv_du[2]
+        v = x.reshape(x.shape[0], -1)
+        y = F.relu(ops.linear(v, c0.weight.view(c0.out_channels, -1), c0.bias))
+        y = torch.sigmoid(ops.linear(y, c2.weight.view(c2.out_channels, -1), c2.bias))
+        return self.bn(v * y + v)
 
 
 def grad_reverse(x, lambd=1.0):
@@ -199,7 +195,7 @@ class Pointnet_c(nn.Module):
         x = self.mlp2(x)
         mid_feature = x
         x = self.dropout2(x)
-        x = ops.linear(x, self.mlp3.weight, self.mlp3.bias) if x.is_cuda else self.mlp3(x)
+        x = ops.linear(x, self.mlp3.weight, self.mlp3.bias)
         if adapt is False or adapt == False:  # noqa: E712  (reference compares with ==)
             return x
         return x, mid_feature

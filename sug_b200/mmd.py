@@ -34,6 +34,8 @@ def mmd_cal(label_s, feat_s, label_t, feat_t, args: dict, data_s=None, data_t=No
         return soft_mmd(label_s, feat_s, label_t, feat_t, float(args["LABEL_SCALE"]), sample_weights=sample_weights)
     elif args["NAME"] == "HARD_MMD":
         return hard_mmd(label_s, feat_s, label_t, feat_t)
+    elif args["NAME"] == "MAX_HARD_MMD":
+        return max_hard_mmd(label_s, feat_s, label_t, feat_t)
     elif args["NAME"] == "OFF":
         return mix_rbf_mmd2(feat_s, feat_t, sigma_list)
     raise RuntimeError("Not Supported MMD Method")
@@ -64,6 +66,49 @@ def hard_mmd(label_s, feat_s, label_t, feat_t):
     """mmd.py:69-77."""
     same = torch.eq(label_s, label_t)
     return mix_rbf_mmd2(feat_s[same], feat_t[same], sigma_list)
+
+
+def get_most_overlapped_element(vec_a, vec_b, num_class=10):
+    """utils/common_utils.py:167-194: per class, pair the first min(count_a, count_b) samples of both label vectors
+    (in the order of a stable sort by label).  Returns two index lists of equal length.  Runs on the labels' device
+    (the reference moves them to the CPU first, mmd.py:100)."""
+    assert int(vec_a.max()) < num_class, "The input class is larger than pre-defined"
+    sa, ia = torch.sort(vec_a.reshape(-1), stable=True)
+    sb, ib = torch.sort(vec_b.reshape(-1), stable=True)
+    ca = torch.bincount(sa, minlength=num_class)[:num_class]
+    cb = torch.bincount(sb, minlength=num_class)[:num_class]
+    take = torch.minimum(ca, cb)
+    # position of every sorted element inside its class run; keep those below the class's pair count
+    ra = torch.arange(sa.numel(), device=sa.device) - (torch.cumsum(ca, 0) - ca)[sa]
+    rb = torch.arange(sb.numel(), device=sb.device) - (torch.cumsum(cb, 0) - cb)[sb.clamp(max=num_class - 1)]
+    keep_a = ra < take[sa]
+    keep_b = (rb < take[sb.clamp(max=num_class - 1)]) & (sb < num_class)
+    return ia[keep_a].tolist(), ib[keep_b].tolist()
+
+
+def max_hard_mmd(label_s, feat_s, label_t, feat_t):
+    """mmd.py:96-105: MMD between the class-matched subsets of both batches."""
+    ind_s, ind_t = get_most_overlapped_element(label_s, label_t)
+    assert len(ind_s) == len(ind_t), "The feature shape mis-matched"
+    return mix_rbf_mmd2(feat_s[ind_s], feat_t[ind_t], sigma_list)
+
+
+def cal_probs2entropy(probs):
+    """dataset_splitter.py:234-241: entropy of rows of probabilities."""
+    return -(probs * torch.log(probs + 1e-30)).sum(1)
+
+
+def entropy_dis(pred_s, pred_t):
+    """mmd.py:161-166."""
+    return kl_divergence_distance(cal_probs2entropy(pred_s), cal_probs2entropy(pred_t))
+
+
+def entropy_weights(pred_s, pred_t, weighting="exp_inverse"):
+    """mmd.py:155-158 (not reachable from mmd_cal in the reference either; kept for API completeness).  With the
+    reference's default weighting the reference itself crashes in distance2weights (a Python list has no reshape);
+    the formula it spells out is implemented."""
+    ops._need_cuda(pred_s, pred_t)
+    return distance2weights(distances=entropy_dis(pred_s, pred_t), method=weighting).reshape(1, -1)
 
 
 def cd_distance(pc1, pc2, chamfer_dist=None, batch_loss=True):
@@ -105,7 +150,8 @@ def normalized(vec):
 def prob_weights_soft(pred_s, pred_t, label_s, label_t, label_weight, weighting="mean2one"):
     """mmd.py:134-148, on the device."""
     assert label_weight < 1, "For Entropy, Label weight should be less than one"
-    if weighting == "mean2one" and pred_s.is_cuda:  # the whole chain below in one launch
+    ops._need_cuda(pred_s, pred_t)
+    if weighting == "mean2one":  # the whole chain below in one launch
         return ops.sda_sem_weights(pred_s, pred_t, label_s.to(pred_s.device), label_t.to(pred_t.device),
                                    label_weight).reshape(1, -1)
     ps = torch.softmax(pred_s.detach().float(), dim=1).view(-1, 10)

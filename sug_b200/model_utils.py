@@ -9,17 +9,9 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 from . import point_utils
-
-
-def exact_conv():
-    """cuDNN convolutions default to TF32 on Ampere+ (``torch.backends.cudnn.allow_tf32``), which
-    costs ~1e-3 relative error per layer; the parity gate of this path is fp32 (rel 1e-3 end to
-    end), so the few remaining library convolutions run with TF32 switched off."""
-    return torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False)
 
 
 class conv_2d(nn.Module):
@@ -38,15 +30,18 @@ class conv_2d(nn.Module):
         self.conv = nn.Sequential(nn.Conv2d(in_ch, out_ch, kernel_size=kernel, bias=bias), nn.BatchNorm2d(out_ch), act)
 
     def forward(self, x):
-        """x [B,Cin,N,1] -> [B,Cout,N,1] like the reference; 1x1 blocks on CUDA run as one fused
-        per-point GEMM + BatchNorm + activation (``forward_pm``), anything else through cuDNN."""
+        """x [B,Cin,N,1] -> [B,Cout,N,1] like the reference: one fused per-point GEMM + BatchNorm + activation
+        (``forward_pm``).  Every conv_2d the reference models instantiate is a 1x1 ReLU / LeakyReLU block on an
+        [B,C,N,1] tensor; anything else (other kernel sizes, the Tanh variant, wider last dimensions) is outside the
+        accelerated path and raises -- there is no library / CPU fallback."""
+        ops._need_cuda(x)
         conv = self.conv[0]
-        if (x.is_cuda and x.dim() == 4 and x.shape[3] == 1 and conv.kernel_size == (1, 1)
+        if not (x.dim() == 4 and x.shape[3] == 1 and conv.kernel_size == (1, 1)
                 and isinstance(self.conv[2], (nn.ReLU, nn.LeakyReLU)) and conv.out_channels % 4 == 0):
-            y = self.forward_pm(x.squeeze(3).transpose(1, 2))
-            return y.transpose(1, 2).unsqueeze(3)
-        with exact_conv():
-            return self.conv(x)
+            raise RuntimeError("conv_2d: only 1x1 ReLU / LeakyReLU blocks on [B,C,N,1] inputs with Cout % 4 == 0 are "
+                               "implemented (the shapes of the reference models); use forward_pm / edgeconv / pool_max")
+        y = self.forward_pm(x.squeeze(3).transpose(1, 2))
+        return y.transpose(1, 2).unsqueeze(3)
 
     def forward_pm(self, x_pm):
         """Point-major version: x_pm [..., Cin] -> [..., Cout]."""
@@ -100,12 +95,11 @@ class fc_layer(nn.Module):
             self.fc = nn.Sequential(nn.Linear(in_ch, out_ch, bias=bias), self.ac)
 
     def forward(self, x):
-        if x.is_cuda:  # the library's fp32-accurate GEMM instead of a cuBLAS SIMT kernel picked for M = batch
-            y = ops.linear(x, self.fc[0].weight, self.fc[0].bias)
-            for m in list(self.fc)[1:]:
-                y = m(y)
-            return y
-        return self.fc(x)
+        # the library's fp32-accurate GEMM (no cuBLAS kernel, no CPU branch); LayerNorm + activation stay in ATen
+        y = ops.linear(x, self.fc[0].weight, self.fc[0].bias)
+        for m in list(self.fc)[1:]:
+            y = m(y)
+        return y
 
 
 class transform_net(nn.Module):
@@ -128,12 +122,9 @@ class transform_net(nn.Module):
         if DGCNN_Flag:
             x = x.max(dim=-1, keepdim=False)[0]
             x = torch.unsqueeze(x, dim=3)
-        if x.is_cuda:
-            x = self.conv2d3.pool_max(x.squeeze(3).transpose(1, 2))
-        else:
-            x = torch.max(self.conv2d3(x), dim=2, keepdim=False)[0]
+        x = self.conv2d3.pool_max(x.squeeze(3).transpose(1, 2))  # conv + BN + ReLU + max over N, fused
         x = x.view(x.size(0), -1)
-        x = self.fc3(self.fc2(self.fc1(x)))
+        x = ops.linear(self.fc2(self.fc1(x)), self.fc3.weight, self.fc3.bias)
         iden = torch.eye(self.K, device=x.device, dtype=x.dtype).view(1, self.K * self.K)
         return (x + iden).view(x.size(0), self.K, self.K)
 
@@ -202,18 +193,11 @@ class focal_loss(nn.Module):
     def forward(self, preds, labels):
         preds = preds.view(-1, preds.size(-1))
         self.alpha = self.alpha.to(preds.device)
-        if preds.is_cuda:
-            # same arithmetic fused into one forward and one backward launch; the reference's statefulness
-            # (alpha re-gathered by the labels on every call, line 168) is kept
-            self.alpha = self.alpha.gather(0, labels.view(-1))
-            return ops.focal_loss(preds, labels.view(-1), self.alpha, float(self.gamma), bool(self.size_average))
-        logsoft = F.log_softmax(preds, dim=1)
-        soft = torch.exp(logsoft).gather(1, labels.view(-1, 1))
-        logsoft = logsoft.gather(1, labels.view(-1, 1))
+        # model_utils.py:164-176 fused into one forward and one backward launch; the reference's statefulness (alpha
+        # re-gathered by the labels on every call, line 168) is kept
+        ops._need_cuda(preds, labels)
         self.alpha = self.alpha.gather(0, labels.view(-1))
-        loss = -torch.mul(torch.pow((1 - soft), self.gamma), logsoft)
-        loss = torch.mul(self.alpha, loss.t())
-        return loss.mean() if self.size_average else loss.sum()
+        return ops.focal_loss(preds, labels.view(-1), self.alpha, float(self.gamma), bool(self.size_average))
 
 
 def knn(x, k):

@@ -208,19 +208,49 @@ def main():
         # ("naive_inverse" / "exp_inverse" build Python lists and crash at mmd.py:202 in the reference)
         w_none = R.mmd.distance2weights(cdv, method="none")
         geo_none = R.mmd.geometric_weights(ds, dt, weighting="none")
-        npz("mmd_modes", hard=hard, off=off, unbiased=unb, lt_same=lt_same, cd=cdv, w_none=w_none, geo_none=geo_none)
+        # MAX_HARD_MMD (mmd.py:96-105) and the entropy distance behind entropy_weights (mmd.py:155-166; with a weighting
+        # the reference can execute -- its default "exp_inverse" crashes at mmd.py:202)
+        max_hard = R.mmd.mmd_cal(ls, Xs, lt, Ys, {"NAME": "MAX_HARD_MMD"})
+        mh_s, mh_t = R.common_utils.get_most_overlapped_element(ls, lt)
+        prob_s, prob_t = torch.softmax(Xs[:, :10], 1), torch.softmax(Ys[:, :10], 1)
+        ent_dis = R.mmd.entropy_dis(prob_s, prob_t)
+        ent_w = R.mmd.entropy_weights(prob_s, prob_t, weighting="mean2one")
+        npz("mmd_modes", hard=hard, off=off, unbiased=unb, lt_same=lt_same, cd=cdv, w_none=w_none, geo_none=geo_none,
+            max_hard=max_hard, mh_s=np.asarray(mh_s), mh_t=np.asarray(mh_t), ent_dis=ent_dis, ent_w=ent_w)
 
-        # ---- whole SUG step (train_dg_single_gpu.py:260-329), B=12, dropout off ----------------
-        Bs = 12  # >= 10: the reference focal_loss re-gathers its own alpha (model_utils.py:168)
-        data, label = O.synth_clouds(Bs, 1024, 0)
-        data_t, label_t = O.synth_clouds(Bs, 1024, 1)
-        net = load_ref_module(R.Model.Net_MDA("DGCNN"), "Net_MDA:DGCNN")
-        net.train()
-        for hd in (net.c1, net.c2):
-            hd.dropout1.p = 0.0
-            hd.dropout2.p = 0.0
-        crit = R.model_utils.focal_loss(num_classes=10, gamma=0.0, alpha=[0.1] * 10)
-        cfg = O.SUG_CFG
+        # ---- whole SUG step (train_dg_single_gpu.py:260-329), dropout off -----------------------------
+        # B = 12 (>= 10: the reference focal_loss re-gathers its own alpha, model_utils.py:168) and B = 64 + 64, the
+        # batch of BASELINE.json configs[1] that bench.py times (needs ~30 GiB of host memory, a few minutes)
+        for name, Bs in (("sug_step", 12), ("sug_step_b64", 64)):
+            if ONLY is not None and name != ONLY:
+                continue
+            if ONLY is None and Bs == 64 and os.environ.get("SUG_GOLDEN_B64", "0") != "1":
+                print("sug_step_b64: skipped (set SUG_GOLDEN_B64=1 or use --only sug_step_b64)")
+                continue
+            ref_step(R, name, Bs)
+
+
+def ref_step(R, name, Bs):
+    data, label = O.synth_clouds(Bs, 1024, 0)
+    data_t, label_t = O.synth_clouds(Bs, 1024, 1)
+    net = load_ref_module(R.Model.Net_MDA("DGCNN"), "Net_MDA:DGCNN")
+    net.train()
+    for hd in (net.c1, net.c2):
+        hd.dropout1.p = 0.0
+        hd.dropout2.p = 0.0
+    crit = R.model_utils.focal_loss(num_classes=10, gamma=0.0, alpha=[0.1] * 10)
+    cfg = O.SUG_CFG
+    # every neighbour list the reference computes, as one 16-bit hash per row of the SORTED list: lets the GPU test
+    # count the rows whose neighbour SET differs from the reference's at full size without storing 40 MB of indices
+    hashes = []
+    ref_knn = R.model_utils.knn
+
+    def knn_rec(x, k):
+        idx = ref_knn(x, k)
+        hashes.append(O.knn_row_hash(idx))
+        return idx
+    R.model_utils.knn = knn_rec
+    try:
         torch.manual_seed(101)
         ps1, ps2, ss1, ss2 = net(data, semantic_adaption=True)
         pt1, pt2, st1, st2 = net(data_t, semantic_adaption=True)
@@ -229,21 +259,44 @@ def main():
         loss_cls = cfg["CLS_WEIGHT"] * (0.5 * loss_s + 0.5 * loss_t)
         fns = net(data, node_adaptation_s=True)
         fnt = net(data_t, node_adaptation_t=True)
-        loss_geo = cfg["MMD_WEIGHT"] * R.mmd.mmd_cal(label, fns, label_t, fnt, cfg["GEO_MMD"], data_s=data, data_t=data_t)
-        l1 = R.mmd.mmd_cal(label, ss1, label_t, st1, cfg["SEM_MMD"], data_s=ps1, data_t=pt1)
-        l2 = R.mmd.mmd_cal(label, ss2, label_t, st2, cfg["SEM_MMD"], data_s=ps2, data_t=pt2)
-        loss_sem = cfg["MMD_WEIGHT"] * (0.5 * l1 + 0.5 * l2)
-        loss = loss_cls + loss_geo + loss_sem
-        loss.backward()
-        grads = {}
-        for n, p in net.named_parameters():
-            if p.grad is not None:
-                grads["gn." + n] = p.grad.norm()
-        keep = ["g.conv1.conv.0.weight", "g.conv2.conv.1.weight", "g.conv4.conv.1.bias", "g.bn5.weight",
-                "g.node_fea_adapt.pred_offset.0.weight", "g.conv1d.bias", "c1.mlp3.weight"]
-        full = {"gf." + n: dict(net.named_parameters())[n].grad for n in keep}
-        npz("sug_step", loss=loss, loss_cls=loss_cls, loss_geo=loss_geo, loss_sem=loss_sem, pred_s1=ps1, pred_t1=pt1,
-            **grads, **full)
+    finally:
+        R.model_utils.knn = ref_knn
+    loss_geo = cfg["MMD_WEIGHT"] * R.mmd.mmd_cal(label, fns, label_t, fnt, cfg["GEO_MMD"], data_s=data, data_t=data_t)
+    l1 = R.mmd.mmd_cal(label, ss1, label_t, st1, cfg["SEM_MMD"], data_s=ps1, data_t=pt1)
+    l2 = R.mmd.mmd_cal(label, ss2, label_t, st2, cfg["SEM_MMD"], data_s=ps2, data_t=pt2)
+    loss_sem = cfg["MMD_WEIGHT"] * (0.5 * l1 + 0.5 * l2)
+    loss = loss_cls + loss_geo + loss_sem
+    loss.backward()
+    grads = {}
+    for n, p in net.named_parameters():
+        if p.grad is not None:
+            grads["gn." + n] = p.grad.norm()
+    keep = ["g.conv1.conv.0.weight", "g.conv2.conv.1.weight", "g.conv4.conv.1.bias", "g.bn5.weight",
+            "g.node_fea_adapt.pred_offset.0.weight", "g.conv1d.bias", "c1.mlp3.weight", "c1.mlp3.bias", "c2.mlp3.weight",
+            "c2.mlp3.bias"]
+    full = {"gf." + n: dict(net.named_parameters())[n].grad for n in keep}
+    extra = {}
+    if Bs > 12:  # the full-size fixture also pins the node / semantic features and the neighbour graphs
+        # ... and carries the gradient norms of the SAME loss with the MMD autograd evaluated in fp64 (oracle; with the
+        # fp32 MMD the oracle reproduces the reference's norms to 1e-6, tests/test_oracle_golden.py): the reference's own
+        # fp32 MMD gradient is cancellation noise for the 4096-d node features, so the parameters
+        # upstream of the MMD cannot be judged against gn.* alone -- the oracle cannot be run at this size on the GPU box
+        rm_conv4, rv_bn5 = net.g.conv4.conv[1].running_mean.clone(), net.g.bn5.running_var.clone()
+        loss = loss.detach().clone()
+        del net, ps2, pt2, ss2, st1, st2, fnt
+        import gc
+        gc.collect()
+        sd = O.clone_state(O.synth_state("Net_MDA:DGCNN"), requires_grad=True)
+        torch.manual_seed(101)
+        out64 = O.sug_losses(sd, data, label, data_t, label_t, O.FocalLoss([0.1] * 10, 0.0), drop_p=0.0, mmd_dtype=torch.float64)
+        out64["loss"].backward()
+        for n, v in sd.items():
+            if v.grad is not None:
+                grads["gn64." + n] = v.grad.norm()
+        extra = dict(knn_hash=torch.stack(hashes).numpy().astype(np.uint16), feat_node_s=fns[:, :64], sem_s1=ss1[:, :32],
+                     rm_conv4=rm_conv4, rv_bn5=rv_bn5)
+    npz(name, loss=loss, loss_cls=loss_cls, loss_geo=loss_geo, loss_sem=loss_sem, pred_s1=ps1, pred_t1=pt1,
+        **grads, **full, **extra)
 
 
 if __name__ == "__main__":
