@@ -115,12 +115,25 @@ int gemm_simt_f32(const float* a, int64_t sam, int64_t sak, const float* b, int6
                   cudaStream_t stream);
 int gemm_tc_f32(const float* a, int64_t lda, int a_mn, const float* b, int64_t ldb, int b_mn, const float* bias,
                 float* c, int64_t ldc, int M, int N, int K, cudaStream_t stream);
+int gemm_tc_stats_f32(const float* a, int64_t lda, int a_mn, const float* b, int64_t ldb, int b_mn, const float* bias,
+                      float* c, int64_t ldc, int M, int N, int K, double* colsums, bool* fused, cudaStream_t stream);
+// gemm_f32 for a K-major A and B (x W^T + bias) that also accumulates the BatchNorm column statistics of C into
+// colsums[2*N] (fp64, zeroed by the caller) when the tensor-core epilogue can do it; *fused reports whether it did.
+int gemm_f32_colstats(const float* a, int64_t lda, const float* b, int64_t ldb, const float* bias, float* c, int64_t ldc,
+                      int M, int N, int K, double* colsums, bool* fused, cudaStream_t stream);
 
 // Per-channel BatchNorm batch statistics -> (mean, invstd), running-stat update.
 // sums: [2*C] doubles (sum, sum of squares) over `count` samples.
 int bn_finalize_stats(const double* sums, int C, double count, float eps, float momentum,
                       float* running_mean, float* running_var, float* save_mean_invstd,
                       cudaStream_t stream);
+// out = act(BN(y)) over [P, Cout] rows (edgeconv.cu): statistics given as (mean, invstd), or finalised from fp64 sums by
+// the kernel itself (which then also writes `save` = (mean, invstd) and updates the running statistics).
+int bn_act_launch(const float* y, const float* gamma, const float* beta, const float* mean_invstd, long long P, int Cout,
+                  float slope, float* out, long long ldo, cudaStream_t stream);
+int bn_act_from_sums_launch(const float* y, const float* gamma, const float* beta, const double* sums, double count, float eps,
+                            float momentum, float* running_mean, float* running_var, float* save, long long P, int Cout,
+                            float slope, float* out, long long ldo, cudaStream_t stream);
 // (mean, invstd) from running statistics (eval mode).
 int bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
                   float* save_mean_invstd, cudaStream_t stream);

@@ -143,15 +143,40 @@ edge_gather_fwd_kernel(const float* __restrict__ ab, const int* __restrict__ idx
 }
 
 // out = act(gamma (ext - mean) invstd + beta), float4 per thread.
+// SUMS: the batch statistics come as fp64 (sum, sum of squares) over `count` samples and are finalised here by every
+// block for itself (Cout divisions); block 0 also writes (mean, invstd) for the backward and updates the running
+// statistics exactly like nn.BatchNorm (momentum, unbiased variance) -- no separate finalize launch.
+template <bool SUMS>
 __global__ void __launch_bounds__(256)
-bn_act_kernel(const float* __restrict__ ext, const float* __restrict__ gamma, const float* __restrict__ beta,
-              const float* __restrict__ mean_invstd, long long P, int Cout, float slope, float* __restrict__ out,
-              long long ldo) {
+bn_act_kernel_t(const float* __restrict__ ext, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float* __restrict__ mean_invstd, const double* __restrict__ sums, double count, float eps,
+                float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                float* __restrict__ save, long long P, int Cout, float slope, float* __restrict__ out, long long ldo) {
   extern __shared__ float ss[];  // scale[Cout], shift[Cout]
   for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
-    float sc = gamma[c] * mean_invstd[Cout + c];
+    float mean_f, is_f;
+    if (SUMS) {
+      const double mean = sums[c] / count;
+      double var = sums[Cout + c] / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mean_f = (float)mean;
+      is_f = (float)(1.0 / sqrt(var + (double)eps));
+      if (blockIdx.x == 0) {
+        save[c] = mean_f;
+        save[Cout + c] = is_f;
+        if (running_mean != nullptr) {
+          const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+          running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+          running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
+        }
+      }
+    } else {
+      mean_f = mean_invstd[c];
+      is_f = mean_invstd[Cout + c];
+    }
+    const float sc = gamma[c] * is_f;
     ss[c] = sc;
-    ss[Cout + c] = beta[c] - mean_invstd[c] * sc;
+    ss[Cout + c] = beta[c] - mean_f * sc;
   }
   __syncthreads();
   const int CQ = Cout >> 2;
@@ -169,6 +194,29 @@ bn_act_kernel(const float* __restrict__ ext, const float* __restrict__ gamma, co
     o.w = act_leaky(fmaf(sc[3], v.w, sh[3]), slope);
     *reinterpret_cast<float4*>(out + i * ldo + 4 * c4) = o;
   }
+}
+
+// launchers shared with pool.cu
+int bn_act_launch(const float* y, const float* gamma, const float* beta, const float* mean_invstd, long long P, int Cout,
+                  float slope, float* out, long long ldo, cudaStream_t stream) {
+  const long long total = P * (Cout >> 2);
+  const int g2 = (int)min((long long)num_sms() * 8, (total + 255) / 256);
+  ProfScope ps(KC_BN_ACT, 2.0 * P * Cout, 8.0 * P * Cout, stream);
+  bn_act_kernel_t<false><<<g2, 256, 2 * Cout * sizeof(float), stream>>>(y, gamma, beta, mean_invstd, nullptr, 0.0, 0.f, 0.f,
+                                                                       nullptr, nullptr, nullptr, P, Cout, slope, out, ldo);
+  SUG_LAUNCH_CHECK();
+  return 0;
+}
+int bn_act_from_sums_launch(const float* y, const float* gamma, const float* beta, const double* sums, double count, float eps,
+                            float momentum, float* running_mean, float* running_var, float* save, long long P, int Cout,
+                            float slope, float* out, long long ldo, cudaStream_t stream) {
+  const long long total = P * (Cout >> 2);
+  const int g2 = (int)min((long long)num_sms() * 8, (total + 255) / 256);
+  ProfScope ps(KC_BN_ACT, 2.0 * P * Cout, 8.0 * P * Cout, stream);
+  bn_act_kernel_t<true><<<g2, 256, 2 * Cout * sizeof(float), stream>>>(y, gamma, beta, nullptr, sums, count, eps, momentum,
+                                                                      running_mean, running_var, save, P, Cout, slope, out, ldo);
+  SUG_LAUNCH_CHECK();
+  return 0;
 }
 
 // ghat = g * act'(z);  G1 += ghat;  G2 += ghat * yhat.
@@ -308,17 +356,10 @@ edge_bwd_main_kernel(const float* __restrict__ ab, const float* __restrict__ gha
 // shared memory, pre-multiplied by sign(gamma) so that "extreme" is always a max.  Because
 // y_ij = a_j + b_i with b_i constant over the k neighbours, the arg-max over y is the arg-max over a,
 // and the BatchNorm sums factor as
-//     sum y   = sum_i (S_i + k b_i),                         S_i = sum_{j in N(i)} a_j
-//     sum y^2 = sum_j deg_j a_j^2 + sum_i (2 b_i S_i + k b_i^2)      (deg_j = in-degree of j)
+//     sum y   = sum_i (S_i + k b_i),                         S_i = sum_{j in N(i)} a_j,  Q_i = sum_{j in N(i)} a_j^2
+//     sum y^2 = sum_i (Q_i + 2 b_i S_i + k b_i^2)
 // so the per-edge work is one conflict-free LDS.128 and, per channel, compare + 2 selects + 1 add.
 // Lanes own 4 channels; a warp serves 32*4/CH points per step; neighbour lists are staged per warp.
-__global__ void knn_degree_kernel(const int* __restrict__ idx, long long E, int N, int k, int* __restrict__ deg) {
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
-    const long long cloud = e / ((long long)N * k);
-    atomicAdd(deg + cloud * N + __ldg(idx + e), 1);
-  }
-}
-
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -328,7 +369,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // KB: bits of the arg-slot code embedded in the keys (0 = exact compare / select path)
 template <int CH, bool TRAIN, int KB>
 __global__ void __launch_bounds__(512, 1)
-edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ idx, const int* __restrict__ deg,
+edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ idx,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
                         const float* __restrict__ mean_invstd, int N, int k, int Cout, float slope,
                         float* __restrict__ ext, uint8_t* __restrict__ arg, float* __restrict__ ssum,
@@ -346,19 +387,14 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
   const int ld = 2 * Cout;
   const long long cb = (long long)b * N;
   const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + (tid % Q));
-  // ---- stage the signed A chunk; deg-weighted sum of squares on the way ----
-  double dsq[4] = {0, 0, 0, 0};
-  for (int e0 = tid; e0 < N * Q; e0 += 4 * 512) {  // 512 % Q == 0  =>  this thread's quad index is fixed
-    float4 vv[4];                                    // four independent loads in flight per thread
-    float dgs[4];
+  // ---- stage the signed A chunk (four independent loads in flight per thread) ----
+  for (int e0 = tid; e0 < N * Q; e0 += 4 * 512) {
+    float4 vv[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const int e = e0 + w * 512;
       const int n = e / Q, qq = e - n * Q;
-      if (e < N * Q) {
-        vv[w] = __ldg(reinterpret_cast<const float4*>(ab + (cb + n) * ld + c0) + qq);
-        if (TRAIN) dgs[w] = (float)__ldg(deg + cb + n);
-      }
+      if (e < N * Q) vv[w] = __ldg(reinterpret_cast<const float4*>(ab + (cb + n) * ld + c0) + qq);
     }
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
@@ -366,13 +402,6 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
       if (e >= N * Q) break;
       const int n = e / Q, qq = e - n * Q;
       float4 v = vv[w];
-      if (TRAIN) {
-        const float dg = dgs[w];
-        dsq[0] += (double)(dg * v.x * v.x);
-        dsq[1] += (double)(dg * v.y * v.y);
-        dsq[2] += (double)(dg * v.z * v.z);
-        dsq[3] += (double)(dg * v.w * v.w);
-      }
       v.x = g4.x < 0.f ? -v.x : v.x;
       v.y = g4.y < 0.f ? -v.y : v.y;
       v.z = g4.z < 0.f ? -v.z : v.z;
@@ -427,6 +456,7 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
       float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       int bslot[4] = {0, 0, 0, 0};
       float s1[4] = {0, 0, 0, 0};
+      float q1[4] = {0, 0, 0, 0};  // sum of a_j^2 over the neighbours: FMA-pipe work, the ALU pipe bounds the loop
       const int* myi = wi + sub * k;
       if (KB == 0) {
         // exact arg: compare + two selects per neighbour and channel (any k <= 255)
@@ -440,7 +470,10 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
             const bool gt = aa[u] > best[u];
             best[u] = gt ? aa[u] : best[u];
             bslot[u] = gt ? s : bslot[u];
-            if (TRAIN) s1[u] += aa[u];
+            if (TRAIN) {
+              s1[u] += aa[u];
+              q1[u] = fmaf(aa[u], aa[u], q1[u]);
+            }
           }
         }
       } else {
@@ -468,6 +501,7 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
               const float k1 = __uint_as_float((__float_as_uint(cc[u]) & ~KM) | code1);
               kbest[u] = fmax3(kbest[u], k0, k1);
               s1[u] += aa[u] + cc[u];
+              q1[u] = fmaf(cc[u], cc[u], fmaf(aa[u], aa[u], q1[u]));
             }
           }
         }
@@ -481,6 +515,7 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
             if (TRAIN) {
               kbest[u] = fmaxf(kbest[u], __uint_as_float((__float_as_uint(aa[u]) & ~KM) | code0));
               s1[u] += aa[u];
+              q1[u] = fmaf(aa[u], aa[u], q1[u]);
             }
           }
         }
@@ -498,7 +533,7 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
         S4[u] = fmaf(kf, bb[u], sa);
         if (TRAIN) {
           ds[u] += (double)S4[u];
-          dq[u] += (double)(2.f * bb[u] * sa + kf * bb[u] * bb[u]);
+          dq[u] += (double)(q1[u] + 2.f * bb[u] * sa + kf * bb[u] * bb[u]);
         }
       }
       if (TRAIN) {
@@ -534,7 +569,7 @@ edge_gather_smem_kernel(const float* __restrict__ ab, const int* __restrict__ id
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       v[u] = ds[u];
-      v[4 + u] = dq[u] + dsq[u];
+      v[4 + u] = dq[u];
     }
 #pragma unroll
     for (int o = 16; o >= Q; o >>= 1)
@@ -856,7 +891,6 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
   float* wcat = W.take<float>(2 * (size_t)Cout * C);
   double* sums = W.take<double>(2 * (size_t)Cout);
   float* mi_eval = W.take<float>(2 * (size_t)Cout);
-  int* deg = W.take<int>((size_t)P);
   if (!W.ok()) { set_error("edgeconv_fwd: workspace too small (%zu B)", ws_bytes); return SUG_E_WORKSPACE; }
 
   {
@@ -872,14 +906,12 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
       ProfScope ps(KC_EDGE_FWD, 4.0 * P * k * Cout, (double)P * (8.0 * Cout + 4.0 * k + 9.0 * Cout), stream);
       const int CH = smem_chunk(B, N, Cout, k);
       if (CH != 0) {
-        SUG_CUDA(cudaMemsetAsync(deg, 0, sizeof(int) * P, stream));
-        knn_degree_kernel<<<num_sms() * 4, 256, 0, stream>>>(idx, (long long)P * k, N, k, deg);
         const size_t sm = smem_bytes_gather(N, CH, k);
 #define SUG_GATHER_T(CH_, KB_)                                                                               \
   do {                                                                                                       \
     SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<CH_, true, KB_>, sm));                            \
     edge_gather_smem_kernel<CH_, true, KB_><<<dim3(Cout / CH_, B), 512, sm, stream>>>(                       \
-        ab, idx, deg, gamma, beta, nullptr, N, k, Cout, slope, ext, arg, ssum, sums, nullptr, 0);            \
+        ab, idx, gamma, beta, nullptr, N, k, Cout, slope, ext, arg, ssum, sums, nullptr, 0);                 \
   } while (0)
         if (CH == 32) {
           if (k <= 32) SUG_GATHER_T(32, 5);
@@ -897,16 +929,8 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
       }
     }
     SUG_LAUNCH_CHECK();
-    SUG_TRY(bn_finalize_stats(sums, Cout, (double)P * k, eps, momentum, running_mean, running_var,
-                              save_mean_invstd, stream));
-    long long total = P * (Cout >> 2);
-    int g2 = (int)min((long long)num_sms() * 8, (total + 255) / 256);
-    {
-      ProfScope ps(KC_BN_ACT, 2.0 * P * Cout, 8.0 * P * Cout, stream);
-      bn_act_kernel<<<g2, 256, 2 * Cout * sizeof(float), stream>>>(ext, gamma, beta, save_mean_invstd, P, Cout, slope,
-                                                                   out, ldo);
-    }
-    SUG_LAUNCH_CHECK();
+    SUG_TRY(bn_act_from_sums_launch(ext, gamma, beta, sums, (double)P * k, eps, momentum, running_mean, running_var,
+                                    save_mean_invstd, P, Cout, slope, out, ldo, stream));
   } else {
     SUG_TRY(bn_eval_stats(running_mean, running_var, Cout, eps, mi_eval, stream));
     {
@@ -916,11 +940,11 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
       if (CH == 32) {
         SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<32, false, 5>, sm));
         edge_gather_smem_kernel<32, false, 5><<<dim3(Cout / 32, B), 512, sm, stream>>>(
-            ab, idx, nullptr, gamma, beta, mi_eval, N, k, Cout, slope, nullptr, nullptr, nullptr, nullptr, out, ldo);
+            ab, idx, gamma, beta, mi_eval, N, k, Cout, slope, nullptr, nullptr, nullptr, nullptr, out, ldo);
       } else if (CH == 16) {
         SUG_TRY(smem_attr((const void*)edge_gather_smem_kernel<16, false, 5>, sm));
         edge_gather_smem_kernel<16, false, 5><<<dim3(Cout / 16, B), 512, sm, stream>>>(
-            ab, idx, nullptr, gamma, beta, mi_eval, N, k, Cout, slope, nullptr, nullptr, nullptr, nullptr, out, ldo);
+            ab, idx, gamma, beta, mi_eval, N, k, Cout, slope, nullptr, nullptr, nullptr, nullptr, out, ldo);
       } else {
         edge_gather_fwd_kernel<false><<<grid, 256, 0, stream>>>(ab, idx, gamma, beta, mi_eval, (int)P, N, k, Cout, slope,
                                                                 nullptr, nullptr, nullptr, nullptr, out, ldo);

@@ -339,6 +339,15 @@ int gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t s
   return gemm_simt_f32(a, sam, sak, b, sbn, sbk, bias, c, ldc, M, N, K, accumulate, stream);
 }
 
+int gemm_f32_colstats(const float* a, int64_t lda, const float* b, int64_t ldb, const float* bias, float* c, int64_t ldc,
+                      int M, int N, int K, double* colsums, bool* fused, cudaStream_t stream) {
+  *fused = false;
+  const bool tc_ok = K >= 16 && N >= 8 && M > 8 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && lda % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(b) & 15) == 0 && ldb % 4 == 0;
+  if (tc_ok) return gemm_tc_stats_f32(a, lda, 0, b, ldb, 0, bias, c, ldc, M, N, K, colsums, fused, stream);
+  return gemm_f32(a, lda, 1, b, ldb, 1, bias, c, ldc, M, N, K, 0, stream);
+}
+
 }  // namespace sug
 
 // Same problem statement as sug_gemm_f32 but through the dispatcher (tensor cores when possible).

@@ -42,7 +42,8 @@ struct TcCfg {
   static constexpr int NEED_COLS = ACC_COLS + (A_TS ? STAGES * 64 : 0);
   static constexpr int TMEM_COLS = NEED_COLS <= 32 ? 32 : NEED_COLS <= 64 ? 64 : NEED_COLS <= 128 ? 128 : NEED_COLS <= 256 ? 256 : 512;
   static_assert(NEED_COLS <= 512, "TMEM overflow");
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*column partials*/;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory plan");
 };
 
 struct TcArgs {
@@ -53,6 +54,8 @@ struct TcArgs {
   int tiles_m, tiles_n, ksplits, kb_per_split;
   int epi;
   int tma_store;  // epilogue through shared memory + cp.async.bulk.tensor (needs an aligned C)
+  double* colsums;  // optional [2*N]: per-column sum and sum of squares of C (BatchNorm statistics), accumulated
+                    // by the epilogue from the staged tiles -- the separate pass over C (col_stats) disappears
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -73,6 +76,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 3 * S;   // [2]  MMA -> epilogue
   uint64_t* tempty = bars + 3 * S + 2;  // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+  float* colpart = reinterpret_cast<float*>(epi_smem + Cfg::EPI_BYTES + 256);  // [4 warps][2][32] column partials
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n * p.ksplits;
@@ -281,6 +285,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             else tma_store_2d(&tmC, buf, col0, mt * TBM + lg * 32);
           }
           if (lane == 0) tma_store_commit();
+          if (p.colsums != nullptr) {
+            // lane c sums column col0 + c over this warp's (valid) rows of the staged tile: the 16 B chunk of
+            // column quad q sits at (q ^ (row & 7)), so the 32 lanes of a row read 32 different banks.  The four
+            // epilogue warps (the four 32-row groups of the tile) combine through 1 KB of shared memory and warp 0
+            // issues the 64 fp64 atomics of the chunk: M/128 instead of M/32 atomics per column.
+            const int nvalid = min(32, p.M - (mt * TBM + lg * 32));
+            const int qq = lane >> 2, e4 = (lane & 3) << 2;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < nvalid; ++r) {
+              const float val = *reinterpret_cast<const float*>(buf + r * 128 + ((qq ^ (r & 7)) << 4) + e4);
+              s1 += val;
+              s2 = fmaf(val, val, s2);
+            }
+            colpart[(warp - 6) * 64 + lane] = s1;
+            colpart[(warp - 6) * 64 + 32 + lane] = s2;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 6) {
+              const int col = col0 + lane;
+              const float t1 = colpart[lane] + colpart[64 + lane] + colpart[128 + lane] + colpart[192 + lane];
+              const float t2 = colpart[32 + lane] + colpart[96 + lane] + colpart[160 + lane] + colpart[224 + lane];
+              if (col < p.N) {
+                atomicAdd(p.colsums + col, (double)t1);
+                atomicAdd(p.colsums + p.N + col, (double)t2);
+              }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
         }
       } else {
         float* crow = p.C + (long long)row * p.ldc;
@@ -376,7 +408,15 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
 // a: K-major -> [M, K] row-major with stride lda; MN-major -> [K, M] row-major with stride lda (same for b / N).
 int gemm_tc_f32(const float* a, int64_t lda, int a_mn, const float* b, int64_t ldb, int b_mn, const float* bias, float* c,
                 int64_t ldc, int M, int N, int K, cudaStream_t stream) {
+  return gemm_tc_stats_f32(a, lda, a_mn, b, ldb, b_mn, bias, c, ldc, M, N, K, nullptr, nullptr, stream);
+}
+
+// Same, optionally accumulating the column sums / sums of squares of C into colsums[2*N] (fp64, zeroed by the
+// caller).  *fused tells whether the epilogue did it (it cannot with split-K or an unaligned C).
+int gemm_tc_stats_f32(const float* a, int64_t lda, int a_mn, const float* b, int64_t ldb, int b_mn, const float* bias,
+                      float* c, int64_t ldc, int M, int N, int K, double* colsums, bool* fused, cudaStream_t stream) {
   SUG_CHECK_ARG(M > 0 && N > 0 && K > 0 && a && b && c, "gemm_tc: bad problem M=%d N=%d K=%d", M, N, K);
+  if (fused != nullptr) *fused = false;
   const int BN = (N <= 64) ? 64 : 128;
   CUtensorMap tmA, tmB, tmC;
   const bool c_tma = (reinterpret_cast<uintptr_t>(c) & 15) == 0 && ldc % 4 == 0;
@@ -401,6 +441,8 @@ int gemm_tc_f32(const float* a, int64_t lda, int a_mn, const float* b, int64_t l
   args.ksplits = cdiv(kb_total, args.kb_per_split);
   args.epi = args.ksplits > 1 ? EPI_ATOMIC : EPI_STORE;
   args.tma_store = c_tma ? 1 : 0;
+  args.colsums = (colsums != nullptr && args.epi == EPI_STORE && c_tma) ? colsums : nullptr;
+  if (fused != nullptr) *fused = args.colsums != nullptr;
   if (args.epi == EPI_ATOMIC) {
     SUG_CHECK_ARG(bias == nullptr, "gemm_tc: bias with split-K is not supported");
     SUG_CUDA(cudaMemset2DAsync(c, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));

@@ -12,13 +12,16 @@
 // Selection is what bounds this kernel (ALU pipe: a streaming sorted-list insert costs ~100 min/max/
 // select per accepted candidate and ~5 k log-many candidates are accepted per row), so the candidates
 // are swept TWICE -- the tensor pipe is nearly idle, recomputing the tile is free:
-//   sweep 0: (over the first half of the cloud's tiles only -- the k-th best of any subset bounds the k-th best
-//            of the whole from below) every thread keeps 32 running maxima (candidate j -> slot j mod 32), sorts
-//            them with a 32-input odd-even merge network and the k-th largest over the row's 64 slot maxima (two
+//   sweep 0: every thread keeps 32 running maxima (candidate j -> slot j mod 32), sorts them with a
+//            32-input odd-even merge network and the k-th largest over the row's 64 slot maxima (two
 //            threads per row, see below) is a lower bound T <= (k-th largest key);
-//   sweep 1: candidates with key >= T (about 2k + 12 per row) are appended to a per-row list in
+//   sweep 1: candidates with key >= T (about k + a few per row) are appended to a per-row list in
 //            shared memory with predicated stores -- no data-dependent loop, no divergence;
 //   final:   rank of every listed candidate by counting, out[rank] = id for rank < k (sorted output).
+// Measured and dropped (round 2, B = 64, N = 1024, C = 64, k = 20, all bit-exact): the threshold sweep over only half
+// of the tiles (the k-th best of a subset is still a valid bound) -- the ~2k + 12 survivors per row make the
+// rank-by-counting and the list prunes quadratically more expensive: 372 us against 168 us; candidate lo tiles
+// precomputed per call and loaded by TMA (a two-party TMA -> MMA ring without the split hop): 172 us, no gain.
 // Two selection groups (4 warps each) alternate over the accumulator buffers, so a query row is served
 // by two threads (one per group) which exchange T, list sizes and lists through shared memory.
 // Key = (-|x_i|^2 + 2 x_i.x_j) - |x_j|^2, the reference's operation order.
@@ -58,7 +61,6 @@ struct KnnTcArgs {
   int* idx;         // [B,N,k]
   int B, N, C, k;
   int mtiles_per_cloud, ntiles;
-  int n0;  // candidate tiles of sweep 0 (the threshold sweep): a prefix of the cloud's tiles
 };
 
 // Shared-memory plan of knn_tc_kernel<K> (offsets from the 1 KB aligned base).
@@ -150,8 +152,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
         __syncwarp();
         mbar_wait(a_ready, mi & 1);  // queries are in TMEM: the ring is free for candidates
         for (int sweep = 0; sweep < 2; ++sweep) {
-          const int nts = sweep == 0 ? p.n0 : p.ntiles;
-          for (int nt = 0; nt < nts; ++nt) {
+          for (int nt = 0; nt < p.ntiles; ++nt) {
             const int gcol = b * p.N + nt * QBN;
             for (int kb = 0; kb < kbs; ++kb, ++it) {
               const int s = it % S;
@@ -174,7 +175,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
       for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x, ++mi) {
         mbar_wait(a_ready, mi & 1);
         tc_fence_after();
-        for (int t = 0; t < p.n0 + p.ntiles; ++t, ++tile_it) {
+        for (int t = 0; t < 2 * p.ntiles; ++t, ++tile_it) {
           const uint32_t ab = tile_it % nacc;
           mbar_wait(&tempty[ab], ((tile_it / nacc) & 1) ^ 1);
           tc_fence_after();
@@ -229,7 +230,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(a_ready);
-      for (int t = 0; t < p.n0 + p.ntiles; ++t) {
+      for (int t = 0; t < 2 * p.ntiles; ++t) {
         for (int kb = 0; kb < kbs; ++kb, ++it) {
           const int s = it % S;
           mbar_wait(&full[s], (it / S) & 1);
@@ -257,8 +258,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
     const float* ov = vals + (size_t)(1 - grp) * CAP * 128;  // the row's other list
     float* xch = vals + (size_t)CAP * 128;                  // group 1's sorted maxima (its list is empty then)
     uint32_t tile_it = 0;  // accumulator tiles issued before the current query block
-    const int ttot = p.n0 + p.ntiles;  // tiles per query block: sweep 0 over the first n0 tiles, sweep 1 over all
-    for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x, tile_it += ttot) {
+    for (int mt = blockIdx.x; mt < total_m; mt += gridDim.x, tile_it += 2 * p.ntiles) {
       const int b = mt / p.mtiles_per_cloud, r0 = (mt % p.mtiles_per_cloud) * 128;
       const int row = r0 + r;
       const long long cbase = (long long)b * p.N;
@@ -271,8 +271,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
 
       // tiles t = 0 .. 2*ntiles-1 (sweep 0 then sweep 1); mine are those that land in accumulator `grp`
       auto load_norm = [&](int t) -> float {
-        const int cj = (t < p.n0 ? t : t - p.n0) * QBN + gt;
-        return (t < ttot && cj < p.N) ? __ldg(p.xx + cbase + cj) : 0.f;
+        const int cj = (t < p.ntiles ? t : t - p.ntiles) * QBN + gt;
+        return (t < 2 * p.ntiles && cj < p.N) ? __ldg(p.xx + cbase + cj) : 0.f;
       };
       int t = (int)((tile_it ^ (uint32_t)grp) & 1u);
       float nx = load_norm(t);
@@ -280,7 +280,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
       bool have_T = false;
 #pragma unroll 1
       for (;;) {
-        if (!have_T && t >= p.n0) {
+        if (!have_T && t >= p.ntiles) {
           // ---- threshold: k-th largest of the row's 64 slot maxima (each is a real candidate) ----
           have_T = true;
           oe_sort<0, 32>(gm);
@@ -305,9 +305,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, KnnTcArgs p) {
           asm volatile("bar.sync 4, 256;" ::: "memory");
           T = fmaxf(tbuf[r], -FLT_MAX);
         }
-        if (t >= ttot) break;
-        const bool sweep1 = t >= p.n0;
-        const int nt = sweep1 ? t - p.n0 : t;
+        if (t >= 2 * p.ntiles) break;
+        const bool sweep1 = t >= p.ntiles;
+        const int nt = sweep1 ? t - p.ntiles : t;
         const uint32_t my_it = tile_it + (uint32_t)t;
         const uint32_t ab = my_it % nacc;
         float* gx = gxx + nbuf * (2 * QBN);  // double-buffered norms: one group barrier per tile
@@ -491,11 +491,6 @@ int knn_tc(const float* x, int B, int C, int N, int k, long long ld, int* idx, v
   a.xx = xx; a.idx = idx; a.B = B; a.N = N; a.C = C; a.k = k;
   a.mtiles_per_cloud = cdiv(N, 128);
   a.ntiles = cdiv(N, QBN);
-  // The k-th best key of ANY subset of the candidates is a valid lower bound of the row's k-th best key, so the
-  // threshold sweep only visits the first half of the tiles (1.5 instead of 2 passes of tensor work and selection);
-  // sweep 1 then keeps ~2k + 12 instead of ~k + 6 survivors per row, still within the lists.  Clouds of fewer than
-  // 4 tiles keep the full first sweep (the slot maxima must outnumber k).
-  a.n0 = a.ntiles >= 4 ? (a.ntiles + 1) / 2 : a.ntiles;
   const int grid = min(num_sms(), B * a.mtiles_per_cloud);
   // algorithmic work (one distance matrix); the kernel computes it twice (two sweeps), which is its own business
   ProfScope ps(KC_KNN_TC, 2.0 * B * (double)N * N * C, 4.0 * B * (double)N * (C + k), stream);

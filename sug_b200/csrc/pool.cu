@@ -337,11 +337,6 @@ pw_bwd_main_kernel(float* __restrict__ y, const float* __restrict__ gout, long l
   }
 }
 
-// defined in edgeconv.cu
-__global__ void bn_act_kernel(const float* __restrict__ ext, const float* __restrict__ gamma,
-                              const float* __restrict__ beta, const float* __restrict__ mean_invstd, long long P,
-                              int Cout, float slope, float* __restrict__ out, long long ldo);
-
 }  // namespace sug
 
 using namespace sug;
@@ -359,30 +354,27 @@ extern "C" int sug_linear_bn_act_fwd(const float* x, int64_t ldx, const float* w
   double* sums = W.take<double>(2 * (size_t)Cout);
   float* mi_eval = W.take<float>(2 * (size_t)Cout);
   if (!W.ok()) { set_error("linear_bn_act_fwd: workspace too small"); return SUG_E_WORKSPACE; }
-  SUG_TRY(gemm_f32(x, ldx, 1, w, Cin, 1, bias, y, Cout, (int)P, Cout, Cin, 0, stream));
   const int gx = cdiv(Cout, PCQ * 4);
   const float* mi = save_mean_invstd;
   if (training) {
     SUG_CHECK_ARG(save_mean_invstd != nullptr, "linear_bn_act_fwd: training needs save_mean_invstd");
     SUG_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cout, stream));
-    int gy = (int)min((long long)num_sms() * 4 / gx + 1, (long long)(P + PRL - 1) / PRL);
-    {
+    bool fused = false;  // BatchNorm sums from the GEMM epilogue when the tensor-core kernel runs
+    SUG_TRY(gemm_f32_colstats(x, ldx, w, Cin, bias, y, Cout, (int)P, Cout, Cin, sums, &fused, stream));
+    if (!fused) {
+      int gy = (int)min((long long)num_sms() * 4 / gx + 1, (long long)(P + PRL - 1) / PRL);
       ProfScope ps(KC_COLSTATS, 3.0 * P * Cout, 4.0 * P * Cout, stream);
       col_stats_kernel<<<dim3(gx, gy), 256, 0, stream>>>(y, P, Cout, sums);
     }
     SUG_LAUNCH_CHECK();
-    SUG_TRY(bn_finalize_stats(sums, Cout, (double)P, eps, momentum, running_mean, running_var, save_mean_invstd, stream));
-  } else {
-    SUG_TRY(bn_eval_stats(running_mean, running_var, Cout, eps, mi_eval, stream));
-    mi = mi_eval;
+    SUG_TRY(bn_act_from_sums_launch(y, gamma, beta, sums, (double)P, eps, momentum, running_mean, running_var,
+                                    save_mean_invstd, P, Cout, slope, out, ldo, stream));
+    return 0;
   }
-  long long total = P * (Cout >> 2);
-  int g2 = (int)min((long long)num_sms() * 8, (total + 255) / 256);
-  {
-    ProfScope ps(KC_BN_ACT, 2.0 * P * Cout, 8.0 * P * Cout, stream);
-    bn_act_kernel<<<g2, 256, 2 * Cout * sizeof(float), stream>>>(y, gamma, beta, mi, P, Cout, slope, out, ldo);
-  }
-  SUG_LAUNCH_CHECK();
+  SUG_TRY(gemm_f32(x, ldx, 1, w, Cin, 1, bias, y, Cout, (int)P, Cout, Cin, 0, stream));
+  SUG_TRY(bn_eval_stats(running_mean, running_var, Cout, eps, mi_eval, stream));
+  mi = mi_eval;
+  SUG_TRY(bn_act_launch(y, gamma, beta, mi, P, Cout, slope, out, ldo, stream));
   return 0;
 }
 
@@ -438,13 +430,14 @@ extern "C" int sug_mlp_pool_fwd(const float* x, int64_t ldx, const float* w, con
   double* sums = W.take<double>(2 * (size_t)Cout);
   float* mi_eval = W.take<float>(2 * (size_t)Cout);
   if (!W.ok()) { set_error("mlp_pool_fwd: workspace too small"); return SUG_E_WORKSPACE; }
-  SUG_TRY(gemm_f32(x, ldx, 1, w, Cin, 1, bias, y, Cout, (int)P, Cout, Cin, 0, stream));
   const int gx = cdiv(Cout, PCQ * 4);
   const float* mi = save_mean_invstd;
   if (training) {
     SUG_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cout, stream));
-    int gy = (int)min((long long)num_sms() * 4 / gx + 1, (P + PRL - 1) / PRL);
-    {
+    bool fused = false;  // BatchNorm sums from the GEMM epilogue when the tensor-core kernel runs
+    SUG_TRY(gemm_f32_colstats(x, ldx, w, Cin, bias, y, Cout, (int)P, Cout, Cin, sums, &fused, stream));
+    if (!fused) {
+      int gy = (int)min((long long)num_sms() * 4 / gx + 1, (P + PRL - 1) / PRL);
       ProfScope ps(KC_COLSTATS, 3.0 * P * Cout, 4.0 * P * Cout, stream);
       col_stats_kernel<<<dim3(gx, gy), 256, 0, stream>>>(y, P, Cout, sums);
     }
@@ -452,6 +445,7 @@ extern "C" int sug_mlp_pool_fwd(const float* x, int64_t ldx, const float* w, con
     SUG_TRY(bn_finalize_stats(sums, Cout, (double)P, eps, momentum, running_mean, running_var, save_mean_invstd,
                               stream));
   } else {
+    SUG_TRY(gemm_f32(x, ldx, 1, w, Cin, 1, bias, y, Cout, (int)P, Cout, Cin, 0, stream));
     SUG_TRY(bn_eval_stats(running_mean, running_var, Cout, eps, mi_eval, stream));
     mi = mi_eval;
   }

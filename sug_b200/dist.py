@@ -35,27 +35,32 @@ def world_size() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
-def allreduce_grads(model: torch.nn.Module):
-    """Average the gradients of every parameter that received one (one flat bucket, one
-    all-reduce).  Parameters the step never touches (g.input_transform_net.*,
-    g.node_fea_adapt.trans.*; 806 793 of 10.9 M) keep ``grad is None`` on every rank, as with the
-    reference's ``find_unused_parameters=True``, so Adam skips them exactly as on one GPU."""
+def grads_of(model: torch.nn.Module):
+    return [p.grad for p in model.parameters() if p.grad is not None]
+
+
+def allreduce_grads(model: torch.nn.Module, grads=None):
+    """Average the gradients of every parameter that received one, IN PLACE, as ONE coalesced NCCL launch
+    (ncclGroupStart / End around one all-reduce per tensor with the AVG reduction: no flatten / unflatten copies, no
+    separate division).  Parameters the step never touches (g.input_transform_net.*, g.node_fea_adapt.trans.*;
+    806 793 of 10.9 M) keep ``grad is None`` on every rank, as with the reference's ``find_unused_parameters=True``
+    (train_dg.py:217), so Adam skips them exactly as on one GPU.  gloo (CPU tests) has neither coalescing nor AVG:
+    there the tensors are reduced one by one and divided."""
     w = world_size()
     if w == 1:
         return
-    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    if grads is None:
+        grads = grads_of(model)
     if not grads:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    flat.div_(w)
-    off = 0
-    views = []
-    for g in grads:
-        n = g.numel()
-        views.append(flat[off:off + n].view_as(g))
-        off += n
-    torch._foreach_copy_(grads, views)
+    if dist.get_backend() == "nccl":
+        with dist._coalescing_manager(device=grads[0].device, async_ops=False):
+            for g in grads:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)
+    else:
+        for g in grads:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            g.div_(w)
 
 
 class _AllGatherRows(torch.autograd.Function):

@@ -96,11 +96,12 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, optimizers, criterion, batch, points, device, cfg=SUG_CFG, mmd_fn=None,
-                 grad_hook=None, warmup=3):
+                 grad_hook=None, warmup=3, nccl_in_graph=False):
         from . import point_utils
         self.model, self.opts, self.crit = model, optimizers, criterion
         self.cfg, self.mmd_fn, self.hook = cfg, (mmd_fn or mmd.mmd_cal), grad_hook
         self.N = points
+        self.nccl_in_graph = bool(nccl_in_graph)
         dev = torch.device(device)
         self.data = torch.zeros(batch, 3, points, 1, device=dev)
         self.data_t = torch.zeros(batch, 3, points, 1, device=dev)
@@ -188,24 +189,20 @@ class GraphedTrainStep:
             if self.hook is None:
                 with torch.cuda.graph(self.graph):
                     self.out = self._body()
+            elif self.nccl_in_graph:
+                # data parallel, one graph: the coalesced gradient all-reduce is captured with the rest (NCCL supports
+                # stream capture; the capture must not be disturbed by the process group's watchdog thread, hence
+                # the thread-local capture mode)
+                with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                    self.out = self._body()
             else:
-                # data parallel: the collective stays OUTSIDE the graphs (graph A: forwards + backward +
-                # flatten; eager NCCL all-reduce of the flat bucket; graph B: average, unflatten, Adam)
-                import torch.distributed as tdist
-                self._tdist = tdist
-                world = tdist.get_world_size()
+                # data parallel, NCCL outside the graphs: graph A = forwards + backward, then ONE eager coalesced
+                # all-reduce (AVG, in place on the gradients: no flatten / unflatten copies), graph B = the optimisers
                 with torch.cuda.graph(self.graph):
                     self.out = self._fwd_bwd()
                     self._grads = [p.grad for p in self.model.parameters() if p.grad is not None]
-                    self._flat = torch.cat([g.reshape(-1) for g in self._grads])
                 self.graph_b = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph_b, pool=self.graph.pool()):
-                    self._flat.div_(world)
-                    off, views = 0, []
-                    for g in self._grads:
-                        views.append(self._flat[off:off + g.numel()].view_as(g))
-                        off += g.numel()
-                    torch._foreach_copy_(self._grads, views)
                     for o in self.opts:
                         o.step()
         finally:
@@ -224,7 +221,69 @@ class GraphedTrainStep:
             if hasattr(o, "sync_lr"):
                 o.sync_lr()
         self.graph.replay()
-        if self.hook is not None:
-            self._tdist.all_reduce(self._flat)
+        if self.hook is not None and not self.nccl_in_graph:
+            self.hook(self.model, self._grads)
             self.graph_b.replay()
+        return self.out
+
+
+class GraphedEval:
+    """An eval-mode forward (``model(x)`` under ``torch.no_grad()``) as one CUDA graph for a fixed input shape --
+    e.g. ``model_pointnet.DGCNN`` at LiDAR scale (BASELINE.json configs[4]: N = 16 384, k = 20), where the ~30 launches
+    of a forward are otherwise paced by the host.  The adapt layer of ``Net_MDA`` draws its FPS start on the CPU; pass
+    ``fps_points`` (= N) to feed those indices from a device buffer so that the draw stays outside the graph.
+
+        fwd = GraphedEval(net.eval(), x_example)      # captures after 2 eager warm-up passes
+        logits = fwd(x)                               # x: host (pinned) or device tensor of the same shape
+    """
+
+    def __init__(self, model, example, fps_points=None, warmup=2):
+        from . import point_utils
+        assert not model.training, "GraphedEval captures an eval-mode forward"
+        self.model = model
+        self.x = example.detach().clone()
+        self._pu = point_utils
+        self.fps_dev = None
+        if fps_points is not None:
+            self.N = int(fps_points)
+            self.fps_dev = torch.zeros(self.x.shape[0], dtype=torch.int32, device=self.x.device)
+            self.fps_host = [torch.zeros(self.x.shape[0], dtype=torch.int32).pin_memory() for _ in range(4)]
+            self.fps_event = [None] * 4
+            self._slot = 0
+        feed = (lambda: self.fps_dev) if self.fps_dev is not None else None
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        self._pu.set_fps_start_feed(feed)
+        try:
+            with torch.cuda.stream(s), torch.no_grad():
+                for _ in range(warmup):
+                    self._draw()
+                    model(self.x)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self._draw()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(self.graph):
+                self.out = model(self.x)
+        finally:
+            self._pu.set_fps_start_feed(None)
+        torch.cuda.synchronize()
+
+    def _draw(self):
+        if self.fps_dev is None:
+            return
+        slot = self._slot
+        self._slot = (slot + 1) % len(self.fps_host)
+        if self.fps_event[slot] is not None:
+            self.fps_event[slot].synchronize()
+        self.fps_host[slot].copy_(torch.randint(0, self.N, (self.fps_host[slot].shape[0],), dtype=torch.long).to(torch.int32))
+        self.fps_dev.copy_(self.fps_host[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.fps_event[slot] = ev
+
+    def __call__(self, x):
+        self.x.copy_(x, non_blocking=True)
+        self._draw()
+        self.graph.replay()
         return self.out
