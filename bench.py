@@ -45,9 +45,14 @@ def parse():
     ap.add_argument("--profile-all", action="store_true", help="time every kernel class (diagnostics)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     ap.add_argument("--nccl-in-graph", type=int, default=-1,
-                    help="data parallel: 1 = capture the NCCL collectives into the step's CUDA graph (one graph per step, "
-                         "required for a graphed --mmd-scope global), 0 = graph A, eager all-reduce, graph B; "
-                         "-1 (default) = 1 for --mmd-scope global, else 0")
+                    help="data parallel: 1 (default, -1) = capture the NCCL collectives into the step's CUDA graph (one graph "
+                         "per step; needed for a graphed --mmd-scope global), 0 = graph A, eager coalesced all-reduce, graph B")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="data parallel with NCCL in the graph: one all-reduce after the backward instead of the grouped "
+                         "all-reduce that overlaps the backward")
+    ap.add_argument("--dp-no-comm", action="store_true",
+                    help="DIAGNOSTIC ONLY (the line is marked invalid): N independent replicas without the gradient "
+                         "all-reduce, to separate communication cost from multi-process interference")
     ap.add_argument("--share-trunk", action="store_true",
                     help="NOT the headline configuration: let the second encoder pass on a batch reuse conv1/conv2 of the "
                          "first (DGCNN.share_trunk); the default times the four full forwards the reference runs")
@@ -209,6 +214,17 @@ def run_reference(args, rank, emit):
     emit(line)
 
 
+def finish(world):
+    """End of a multi-rank run.  CUDA graphs that hold captured NCCL kernels keep the communicator busy in
+    ProcessGroupNCCL's eyes, and destroy_process_group() then waits forever (measured: the process had to be killed);
+    the JSON line is already on the real stdout (os.write), so the ranks leave without the collective teardown."""
+    if world > 1:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def torch_gpu_reference(dev, B, steps=3):
     """The reference ALGORITHM on this GPU: the oracle's plain PyTorch ops (torch.topk on the materialised N x N
     matrix, the [B,2C,N,k] edge tensor, cuDNN / cuBLAS convolutions, Python FPS loop with its host syncs) moved to the
@@ -320,7 +336,7 @@ def _main(args, rank, emit):
     opts = step.make_optimizers(model, capturable=not args.no_graph)
     crit = model_utils.focal_loss(num_classes=10, gamma=0.0, alpha=[0.1] * 10)  # ClassWeighting / DLSA, uniform counts
     mmd_fn = sdist.global_mmd_cal if (args.mmd_scope == "global" and world > 1) else None
-    hook = sdist.allreduce_grads if world > 1 else None
+    hook = sdist.allreduce_grads if (world > 1 and not args.dp_no_comm) else None
 
     # host batches (pinned) -- a small pool so that every step copies fresh memory
     pool = []
@@ -372,14 +388,14 @@ def _main(args, rank, emit):
     _lib.prof_reset(mask=prof_mask)
     graphed, mode = None, "eager"
     trace(f"dominant class {dom}; building the graphed step")
-    nccl_in_graph = (args.mmd_scope == "global") if args.nccl_in_graph < 0 else bool(args.nccl_in_graph)
+    nccl_in_graph = True if args.nccl_in_graph < 0 else bool(args.nccl_in_graph)
     nccl_in_graph = nccl_in_graph and world > 1
     if not args.no_graph and (mmd_fn is None or nccl_in_graph):  # a collective inside the forward needs NCCL capture
         try:
             for o in opts:
                 o.zero_grad(set_to_none=True)
             graphed = step.GraphedTrainStep(model, opts, crit, B, N_POINTS, dev, mmd_fn=mmd_fn, grad_hook=hook,
-                                            nccl_in_graph=nccl_in_graph)
+                                            nccl_in_graph=nccl_in_graph, overlap=not args.no_overlap)
             graphed.warm(*dev_batches[0])
             _lib.prof_reset(mask=prof_mask)  # count / time exactly the launches recorded into the graph
             graphed.capture()
@@ -452,8 +468,7 @@ def _main(args, rank, emit):
             tdist.all_reduce(hi, op=tdist.ReduceOp.MAX)
             replicas_in_sync = bool(torch.equal(lo, hi))
     if rank != 0:
-        if world > 1:
-            tdist.destroy_process_group()
+        finish(world)
         return
 
     # ---- roofline of the dominant kernel class --------------------------------------------------------
@@ -531,6 +546,8 @@ def _main(args, rank, emit):
             "kernel_ms_one_step": breakdown}
     if replicas_in_sync is not None:
         line["replicas_in_sync"] = replicas_in_sync
+    if args.dp_no_comm:
+        line["diagnostic"] = "no gradient all-reduce: NOT a valid data-parallel number"
 
     if world == 1 and not args.no_torch_reference:
         # free this arm's graph pools first: the reference algorithm keeps ~50 GB of activations at 64+64
@@ -556,8 +573,7 @@ def _main(args, rank, emit):
                                 "sample": f"SUG step at {bs}+{bs} clouds x {N_POINTS} pts (sample of the 64+64 step), "
                                           f"1 warm-up + best of 2, oracle/sug_oracle.py on {step_cpu.threads} host threads"}
     emit(line)
-    if world > 1:
-        tdist.destroy_process_group()
+    finish(world)
 
 
 if __name__ == "__main__":

@@ -63,6 +63,80 @@ def allreduce_grads(model: torch.nn.Module, grads=None):
             g.div_(w)
 
 
+class OverlappedGradAllReduce:
+    """Gradient all-reduce that starts while the backward is still running (what DistributedDataParallel's buckets
+    do for the reference, train_dg.py:216-217), written for a step that is captured into ONE CUDA graph.
+
+    The parameters are grouped by WHEN their gradient is complete in the SUG step's backward:
+      group 0  attention_s / attention_t  (8.4 M of the 10.1 M trained parameters: used by the node passes only, their
+               gradients are final right after the MMD backward, before any encoder backward has run),
+      group 1  the classifier heads c1 / c2 (final once both semantic passes have been back-propagated through them),
+      group 2  the encoder g (final at the very end).
+    A post-accumulate-grad hook counts the finished parameters of each group; the group's coalesced in-place AVG
+    all-reduce is issued on a side stream the moment the count is complete (fork / join edges when captured), so
+    only the last, small group (4.7 MB) is exposed.  ``finish()`` joins the side stream and must be called after
+    ``backward()`` and before the optimisers."""
+
+    def __init__(self, model: torch.nn.Module):
+        groups = [[], [], []]
+        for name, p in model.named_parameters():
+            if name.startswith("attention_"):
+                groups[0].append(p)
+            elif name.startswith("c1.") or name.startswith("c2."):
+                groups[1].append(p)
+            else:
+                groups[2].append(p)
+        self.groups = groups
+        self.need = None          # parameters of each group that receive a gradient (known after one backward)
+        self.count = [0] * len(groups)
+        self.launched = [False] * len(groups)
+        self.side = None
+        self.enabled = False
+        for gi, ps in enumerate(groups):
+            for p in ps:
+                p.register_post_accumulate_grad_hook(lambda _p, gi=gi: self._ready(gi))
+
+    def calibrate(self):
+        """Call once after a backward: records which parameters take part."""
+        self.need = [sum(1 for p in ps if p.grad is not None) for ps in self.groups]
+
+    def begin(self):
+        """Call before ``backward()``."""
+        self.count = [0] * len(self.groups)
+        self.launched = [False] * len(self.groups)
+        self.enabled = self.need is not None and world_size() > 1
+        if self.enabled and self.side is None:
+            self.side = torch.cuda.Stream()
+
+    def _launch(self, gi):
+        grads = [p.grad for p in self.groups[gi] if p.grad is not None]
+        self.launched[gi] = True
+        if not grads:
+            return
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            allreduce_grads(None, grads)
+
+    def _ready(self, gi):
+        if not self.enabled:
+            return
+        self.count[gi] += 1
+        if self.count[gi] == self.need[gi] and not self.launched[gi]:
+            self._launch(gi)
+
+    def finish(self):
+        """Call after ``backward()``: reduces whatever has not been launched and joins the side stream."""
+        if not self.enabled:
+            return False
+        for gi in range(len(self.groups)):
+            if not self.launched[gi]:
+                self._launch(gi)
+        torch.cuda.current_stream().wait_stream(self.side)
+        self.enabled = False
+        return True
+
+
 class _AllGatherRows(torch.autograd.Function):
     """[m, D] per rank -> [W*m, D]; every rank then evaluates the same global loss, so the backward
     hands each rank its own slice scaled by W (the gradient average divides it back)."""

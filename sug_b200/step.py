@@ -96,12 +96,18 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, optimizers, criterion, batch, points, device, cfg=SUG_CFG, mmd_fn=None,
-                 grad_hook=None, warmup=3, nccl_in_graph=False):
+                 grad_hook=None, warmup=3, nccl_in_graph=False, overlap=True):
         from . import point_utils
         self.model, self.opts, self.crit = model, optimizers, criterion
         self.cfg, self.mmd_fn, self.hook = cfg, (mmd_fn or mmd.mmd_cal), grad_hook
         self.N = points
         self.nccl_in_graph = bool(nccl_in_graph)
+        # one graph with NCCL inside: the all-reduce is issued group by group from gradient hooks and overlaps the
+        # remaining backward (dist.OverlappedGradAllReduce); the first eager warm-up step calibrates it
+        self.overlap = None
+        if self.nccl_in_graph and grad_hook is not None and overlap:
+            from .dist import OverlappedGradAllReduce
+            self.overlap = OverlappedGradAllReduce(model)
         dev = torch.device(device)
         self.data = torch.zeros(batch, 3, points, 1, device=dev)
         self.data_t = torch.zeros(batch, 3, points, 1, device=dev)
@@ -130,13 +136,19 @@ class GraphedTrainStep:
         if self._alpha0 is not None:
             self.crit.alpha = self._alpha0
         out = sug_losses(self.model, self.data, self.label, self.data_t, self.label_t, self.crit, self.cfg, self.mmd_fn)
+        if self.overlap is not None:
+            self.overlap.begin()
         out["loss"].backward()
         return {k: v.detach() for k, v in out.items()}
 
     def _body(self):
         out = self._fwd_bwd()
-        if self.hook is not None:
+        if self.overlap is not None and self.overlap.finish():
+            pass  # the gradient all-reduce ran group by group behind the backward
+        elif self.hook is not None:
             self.hook(self.model)
+        if self.overlap is not None and self.overlap.need is None:
+            self.overlap.calibrate()
         for o in self.opts:
             o.step()
         return out
