@@ -53,11 +53,14 @@ col_stats_kernel(const float* __restrict__ y, long long P, int Cout, double* __r
   }
 }
 
-// grid (Cout/128, B).  out[b, c] = act(scale*ext+shift); POOL_MAX_AVG: out[b, Cout+c] = mean_n act(.)
+// grid (Cout/128, B, nsplit).  out[b, c] = act(scale*ext+shift); POOL_MAX_AVG: out[b, Cout+c] = mean_n act(.)
+// nsplit > 1 (few clouds, many points: LiDAR-scale inference): every z-slice reduces its share of the N points and
+// writes (signed extreme, arg, sum) partials; pool_combine_kernel finishes.
 __global__ void __launch_bounds__(256)
 pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float* __restrict__ mean_invstd, int N, int Cout, float slope, int pool,
-                float* __restrict__ out, int* __restrict__ argext) {
+                float* __restrict__ out, int* __restrict__ argext, float* __restrict__ part_ext,
+                int* __restrict__ part_arg, float* __restrict__ part_sum) {
   __shared__ float s_ext[PRL][PCQ * 4];
   __shared__ int s_arg[PRL][PCQ * 4];
   __shared__ float s_sum[PRL][PCQ * 4];
@@ -65,6 +68,9 @@ pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, co
   const int c4l = tid % PCQ, rl = tid / PCQ;
   const int c4 = blockIdx.x * PCQ + c4l;
   const int b = blockIdx.y;
+  const int nsplit = gridDim.z, zs = blockIdx.z;
+  const int per = (N + nsplit - 1) / nsplit;
+  const int n_lo = zs * per, n_hi = min(N, n_lo + per);
   const bool active = 4 * c4 < Cout;
   float sc[4], sh[4], sg[4];
   float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -80,7 +86,7 @@ pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, co
       sg[u] = g < 0.f ? -1.f : 1.f;
     }
     const float* yb = y + (long long)b * N * Cout;
-    for (int n = rl; n < N; n += PRL) {
+    for (int n = n_lo + rl; n < n_hi; n += PRL) {
       float4 v = __ldg(reinterpret_cast<const float4*>(yb + (long long)n * Cout) + c4);
       const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -110,6 +116,13 @@ pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, co
         if (v > bv || (v == bv && a < ba)) { bv = v; ba = a; }
         sm += s_sum[r][tid];
       }
+      if (nsplit > 1) {
+        const long long o = ((long long)b * nsplit + zs) * Cout + c;
+        part_ext[o] = bv;
+        part_arg[o] = ba;
+        part_sum[o] = sm;
+        return;
+      }
       float g = __ldg(gamma + c);
       float scl = g * __ldg(mean_invstd + Cout + c);
       float shf = __ldg(beta + c) - __ldg(mean_invstd + c) * scl;
@@ -120,6 +133,32 @@ pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, co
       if (argext != nullptr) argext[(long long)b * Cout + c] = ba;
     }
   }
+}
+
+__global__ void pool_combine_kernel(const float* __restrict__ part_ext, const int* __restrict__ part_arg,
+                                    const float* __restrict__ part_sum, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean_invstd, int B, int N,
+                                    int Cout, int nsplit, float slope, int pool, float* __restrict__ out,
+                                    int* __restrict__ argext) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * Cout) return;
+  const int b = e / Cout, c = e - b * Cout;
+  float bv = -INFINITY, sm = 0.f;
+  int ba = 0;
+  for (int z = 0; z < nsplit; ++z) {  // slices are in ascending point order: ties keep the lower index
+    const long long o = ((long long)b * nsplit + z) * Cout + c;
+    const float v = part_ext[o];
+    if (v > bv) { bv = v; ba = part_arg[o]; }
+    sm += part_sum[o];
+  }
+  const float g = __ldg(gamma + c);
+  const float scl = g * __ldg(mean_invstd + Cout + c);
+  const float shf = __ldg(beta + c) - __ldg(mean_invstd + c) * scl;
+  const float ev = g < 0.f ? -bv : bv;
+  const int OW = pool == SUG_POOL_MAX_AVG ? 2 * Cout : Cout;
+  out[(long long)b * OW + c] = act_leaky(fmaf(scl, ev, shf), slope);
+  if (pool == SUG_POOL_MAX_AVG) out[(long long)b * OW + Cout + c] = sm / (float)N;
+  if (argext != nullptr) argext[(long long)b * Cout + c] = ba;
 }
 
 // dz_nc = act'(z_nc) * (gavg_bc / N + [n == argext_bc] gmax_bc)
@@ -411,8 +450,15 @@ extern "C" int sug_linear_bn_act_bwd(const float* gout, int64_t ldg, const float
 }
 
 extern "C" size_t sug_mlp_pool_ws_bytes(int B, int N, int Cin, int Cout) {
-  (void)B; (void)N; (void)Cin;
-  return align_up(sizeof(double) * 2 * (size_t)Cout, 256) + align_up(sizeof(float) * 2 * (size_t)Cout, 256) + 1024;
+  (void)Cin;
+  // statistics + (few clouds, many points: the reduction over N is split) partial (extreme, arg, sum) slices
+  const long long gx = cdiv(Cout, PCQ * 4), blocks = gx * B, sms2 = 2LL * num_sms();
+  size_t parts = 0;
+  if (blocks < sms2) {
+    const long long nsplit = min((sms2 + blocks - 1) / blocks, (long long)(N + 255) / 256);
+    if (nsplit > 1) parts = 3 * align_up(sizeof(float) * (size_t)B * Cout * (size_t)nsplit, 256);
+  }
+  return align_up(sizeof(double) * 2 * (size_t)Cout, 256) + align_up(sizeof(float) * 2 * (size_t)Cout, 256) + parts + 1024;
 }
 
 extern "C" int sug_mlp_pool_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* gamma,
@@ -449,9 +495,28 @@ extern "C" int sug_mlp_pool_fwd(const float* x, int64_t ldx, const float* w, con
     SUG_TRY(bn_eval_stats(running_mean, running_var, Cout, eps, mi_eval, stream));
     mi = mi_eval;
   }
+  // few clouds with many points: split N over grid.z so that the reduction still fills the GPU
+  int nsplit = 1;
+  if ((long long)gx * B < 2LL * num_sms()) {
+    nsplit = (int)min((long long)(2 * num_sms() + gx * B - 1) / ((long long)gx * B), (long long)(N + 255) / 256);
+    if (nsplit < 1) nsplit = 1;
+  }
+  float* part_ext = nullptr;
+  int* part_arg = nullptr;
+  float* part_sum = nullptr;
+  if (nsplit > 1) {
+    part_ext = W.take<float>((size_t)B * nsplit * Cout);
+    part_arg = W.take<int>((size_t)B * nsplit * Cout);
+    part_sum = W.take<float>((size_t)B * nsplit * Cout);
+    if (!W.ok()) nsplit = 1;  // workspace of an older caller: fall back to the unsplit reduction
+  }
   {
     ProfScope ps(KC_POOL_FWD, 5.0 * P * Cout, 4.0 * P * Cout, stream);
-    pool_fwd_kernel<<<dim3(gx, B), 256, 0, stream>>>(y, gamma, beta, mi, N, Cout, slope, pool, out, argext);
+    pool_fwd_kernel<<<dim3(gx, B, nsplit), 256, 0, stream>>>(y, gamma, beta, mi, N, Cout, slope, pool, out, argext, part_ext,
+                                                             part_arg, part_sum);
+    if (nsplit > 1)
+      pool_combine_kernel<<<cdiv((long long)B * Cout, 256), 256, 0, stream>>>(part_ext, part_arg, part_sum, gamma, beta, mi, B, N,
+                                                                             Cout, nsplit, slope, pool, out, argext);
   }
   SUG_LAUNCH_CHECK();
   return 0;

@@ -30,7 +30,7 @@ def timeit(fn, iters=10):
 print("| op | N | k | C->Cout | B | time us | alg GB/s (% HBM) | alg TFLOP/s (% bf16) |")
 print("|---|---|---|---|---|---|---|---|")
 QUICK = "--quick" in sys.argv  # step shapes only (B = 64, N = 1024, k = 20), no LiDAR-scale inference
-for N in ((1024,) if QUICK else (1024, 2048, 4096)):
+for N in (() if "--lidar" in sys.argv else (1024,) if QUICK else (1024, 2048, 4096)):
     B = 65536 // N
     for k in ((20,) if QUICK else (20, 40)):
         for C, Co in ((3, 64), (64, 64), (64, 128), (128, 256)):
@@ -63,7 +63,7 @@ for N in ((1024,) if QUICK else (1024, 2048, 4096)):
             by = B * N * (4.0 * (2 * Co + 2 * C) + 4.0 * k + Co)
             print(f"| edgeconv bwd | {N} | {k} | {C}->{Co} | {B} | {t2*1e6:.1f} | {by/t2/1e9:.0f} ({100*by/t2/1e9/peaks['hbm_gbs']:.1f}%) | {3*fl/t2/1e12:.1f} |")
 
-if QUICK:
+if QUICK and "--lidar" not in sys.argv:
     sys.exit(0)
 # configs[4]: LiDAR-scale inference, N = 16384, k = 20 (the reference would need four 1.07 GB N x N tensors per cloud)
 net = model_pointnet.DGCNN().to(dev).eval()
@@ -72,3 +72,13 @@ for B in (1, 4):
     with torch.no_grad():
         t = timeit(lambda: net(x), iters=5)
     print(f"| DGCNN inference (model_pointnet.DGCNN, eval) | 16384 | 20 | - | {B} | {t*1e6:.0f} | {B/t:.1f} clouds/s | peak mem {torch.cuda.max_memory_allocated()/2**30:.2f} GiB |")
+    from sug_b200 import step as _step, _lib as _l
+    fwd = _step.GraphedEval(net, x)
+    t = timeit(lambda: fwd(x), iters=5)
+    print(f"| same, one CUDA graph (step.GraphedEval) | 16384 | 20 | - | {B} | {t*1e6:.0f} | {B/t:.1f} clouds/s | |")
+    if B == 1:
+        _l.prof_reset(mask=0xFFFFFFFF)
+        with torch.no_grad():
+            net(x)
+        pr = _l.prof_collect()
+        print("| per-class us of one eager forward: " + ", ".join(f"{k} {v['ms']*1e3:.0f}" for k, v in pr.items() if v["launches"]) + " | | | | | | | |")
