@@ -64,7 +64,7 @@ def peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return {"hbm": d["hbm_gbs"], "tensor": d["bf16_tflops_sustained"], "tensor_burst": d["bf16_tflops"],
-                "src": "measured"}
+                "sm_max_mhz": d.get("sm_max_mhz", 1965.0), "src": "measured"}
     return {"hbm": 6650.0, "tensor": 1400.0, "tensor_burst": 1590.0, "src": "fallback"}
 
 
@@ -479,7 +479,6 @@ def _main(args, rank, emit):
         # graph replays re-record the same event pairs: the totals are those of the LAST timed step
         d = dict(d, launches=d["timed"], flops=d["flops"], bytes=d["bytes"])
     per_launch_s = (d["ms"] / 1e3) / max(1, d["timed"])
-    GEMM_LIKE = ("gemm_simt", "gemm_tc", "knn_simt", "knn_tc")
 
     # Every tensor-core kernel of this library is fp32-accurate 3xTF32 (hi/lo split, three kind::tf32 products per
     # algorithmic product: the parity gate is fp32), so its tensor roofline is a third of the dense TF32 rate -- measured
@@ -487,20 +486,27 @@ def _main(args, rank, emit):
     # derived from the driver-written file).  FLOPs are counted once (algorithmic), never three times.
     tensor_ceiling = tf32_peak / 3.0
 
+    TENSOR_CORE = ("gemm_tc", "knn_tc")          # tcgen05 kernels
+    SIMT_MATH = ("gemm_simt", "knn_simt")        # CUDA-core distance / GEMM kernels: fp32 pipe, 2 x 128 lanes x SMs x clock
+    fp32_simt_peak = 2.0 * 128 * 148 * (pk.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
+
     def judge(name, flops_pl, bytes_pl, sec):
-        """A GEMM-class kernel is judged against whichever roofline binds it harder at the measured peaks."""
-        t_tensor = flops_pl / (tensor_ceiling * 1e12) if name in GEMM_LIKE else 0.0
+        """A kernel is judged against whichever roofline binds it harder at the measured peaks: HBM copy bandwidth,
+        the 3xTF32 tensor ceiling (tcgen05 kernels) or -- by-class block only -- the nominal fp32 CUDA-core rate."""
         t_hbm = bytes_pl / (pk["hbm"] * 1e9)
         tfl, gbs = flops_pl / sec / 1e12, bytes_pl / sec / 1e9
-        if t_tensor > t_hbm:
+        if name in TENSOR_CORE and flops_pl / (tensor_ceiling * 1e12) > t_hbm:
             r = {"bound": "tensor", "achieved": tfl, "peak": tensor_ceiling, "unit": "TFLOP/s", "frac": tfl / tensor_ceiling,
                  "peak_source": "measured here: dense TF32 torch.matmul / 3 (fp32-accurate 3xTF32 split); "
                                 f"MEASURED_PEAKS bf16 sustained / 6 = {pk['tensor'] / 6.0:.0f}"}
+        elif name in SIMT_MATH and flops_pl / (fp32_simt_peak * 1e12) > t_hbm:
+            r = {"bound": "fp32_simt", "achieved": tfl, "peak": fp32_simt_peak, "unit": "TFLOP/s", "frac": tfl / fp32_simt_peak,
+                 "peak_source": "nominal: 148 SMs x 128 lanes x 2 flop x max SM clock (not a measured peak)"}
         else:
             r = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                  "peak_source": pk["src"] + " copy"}
         r.update({"tflops": tfl, "gbps": gbs, "frac_of_hbm": gbs / pk["hbm"]})
-        if name in GEMM_LIKE:
+        if name in TENSOR_CORE:
             r["frac_of_3xtf32_ceiling"] = tfl / tensor_ceiling
             r["frac_of_bf16_sustained"] = tfl / pk["tensor"]
         return r
