@@ -257,6 +257,14 @@ int sug_focal_loss_bwd(const float* gout, const float* preds, const int64_t* lab
  *                 float) is incremented first, `lr` is read from device memory, so the call can be
  *                 captured in a CUDA graph and follows LR schedulers without re-capture.
  * ------------------------------------------------------------------------------------------- */
+/* sug_adam_multi_f32: the same update for ALL param groups of an optimizer in one launch (the trainer's optimizer_g has
+ * one group per parameter, train_dg_single_gpu.py:191).  Per TENSOR: step_ptrs / lr_ptrs = device addresses of its group's
+ * step counter and learning rate, hyper[4*t .. 4*t+3] = (beta1, beta2, eps, weight_decay); group_step_ptrs [n_groups] =
+ * the distinct step counters, each incremented once before the update.  torch.optim.Adam semantics per group. */
+int sug_adam_multi_f32(const int64_t* p_ptrs, const int64_t* g_ptrs, const int64_t* m_ptrs, const int64_t* v_ptrs,
+                       const int64_t* sizes, const int64_t* step_ptrs, const int64_t* lr_ptrs, const float* hyper,
+                       const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, long long n_params,
+                       const int64_t* group_step_ptrs, int n_groups, sug_stream_t stream);
 int sug_adam_chunk(void);
 int sug_adam_f32(const int64_t* p_ptrs, const int64_t* g_ptrs, const int64_t* m_ptrs, const int64_t* v_ptrs,
                  const int64_t* sizes, const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks,

@@ -59,6 +59,7 @@ SIGNATURES = {
     "sug_focal_loss_bwd": (I, [P, P, P, P, I, I, F, I, P, P]),
     "sug_adam_chunk": (I, []),
     "sug_adam_f32": (I, [P, P, P, P, P, P, P, I, L, P, P, F, F, F, F, P]),
+    "sug_adam_multi_f32": (I, [P, P, P, P, P, P, P, P, P, P, I, L, P, I, P]),
     "sug_prof_num_classes": (I, []),
     "sug_prof_class_name": (c_char_p, [I]),
     "sug_prof_enable": (None, [ctypes.c_uint]),

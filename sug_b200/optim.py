@@ -1,5 +1,6 @@
 """``FusedAdam``: torch.optim.Adam semantics (the optimizer of train_dg_single_gpu.py:191-203) as ONE
-multi-tensor CUDA launch per step (``sug_adam_f32``, csrc/optim.cu).
+multi-tensor CUDA launch per step for ALL param groups (``sug_adam_multi_f32``, csrc/optim.cu; the trainer's optimizer_g
+has one group per parameter).
 
 Same update rule as ``torch.optim.Adam`` (L2 ``weight_decay`` folded into the gradient, bias-corrected
 moments, ``amsgrad=False``), same skipping of parameters whose ``.grad`` is ``None``, same
@@ -26,6 +27,8 @@ class _GroupPlan:
         self.blk = None         # device int32 [2, n_blocks]
         self.n_blocks = 0
         self.n_params = 0
+        self.n_groups = 0
+        self.offsets = None
         self.stages = []        # pinned staging buffers [h_tab, h_blk, event, frozen]; a captured graph
                                 # re-reads its (frozen) buffer at every replay, so those are never reused
         self.keep = None
@@ -74,48 +77,73 @@ class FusedAdam(torch.optim.Optimizer):
                 gs["lr"].fill_(float(group["lr"]))
                 gs["lr_host"] = float(group["lr"])
 
-    def _plan(self, gi, group, gs):
-        ps = [p for p in group["params"] if p.grad is not None]
-        for p in ps:
-            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
-                raise RuntimeError("FusedAdam runs on contiguous fp32 CUDA parameters only (there is no CPU fallback)")
-            if p.grad.is_sparse:
-                raise RuntimeError("FusedAdam does not support sparse gradients")
-            st = self.state[p]
-            if not st:
-                st["step"] = gs["step"]
-                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-        plan = self._plans.setdefault(gi, _GroupPlan())
+    def _plan_all(self, live):
+        """One set of device tables for ALL param groups with gradients (``live`` = [(gi, group, gs)])."""
+        ps, owner = [], []
+        for gi, group, gs in live:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("FusedAdam runs on contiguous fp32 CUDA parameters only (there is no CPU fallback)")
+                if p.grad.is_sparse:
+                    raise RuntimeError("FusedAdam does not support sparse gradients")
+                st = self.state[p]
+                if not st:
+                    st["step"] = gs["step"]
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                ps.append(p)
+                owner.append((group, gs))
+        plan = self._plans.setdefault("all", _GroupPlan())
         grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in ps]
-        # every pointer the device tables hold: a fresh .grad, or moments replaced by load_state_dict, rebuilds them
+        # every pointer / hyper-parameter the device tables hold: a fresh .grad, moments replaced by load_state_dict
+        # or an edited group rebuilds them
         sig = tuple((p.data_ptr(), g.data_ptr(), self.state[p]["exp_avg"].data_ptr(), self.state[p]["exp_avg_sq"].data_ptr(),
-                     p.numel()) for p, g in zip(ps, grads))
+                     p.numel(), gs["step"].data_ptr(), gs["lr"].data_ptr(), tuple(group["betas"]), group["eps"],
+                     group["weight_decay"]) for p, g, (group, gs) in zip(ps, grads, owner))
         if sig != plan.sig:
             dev = ps[0].device if ps else None
             rows = [[p.data_ptr() for p in ps], [g.data_ptr() for g in grads],
                     [self.state[p]["exp_avg"].data_ptr() for p in ps],
-                    [self.state[p]["exp_avg_sq"].data_ptr() for p in ps], [p.numel() for p in ps]]
+                    [self.state[p]["exp_avg_sq"].data_ptr() for p in ps], [p.numel() for p in ps],
+                    [gs["step"].data_ptr() for _, gs in owner], [gs["lr"].data_ptr() for _, gs in owner]]
+            steps = sorted({gs["step"].data_ptr() for _, gs in owner})
+            hyper = [[float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"])] for g, _ in owner]
             bt, bc = [], []
             for t, p in enumerate(ps):
                 nchunk = (p.numel() + self._chunk - 1) // self._chunk
                 bt.extend([t] * nchunk)
                 bc.extend(range(nchunk))
-            plan.n_blocks, plan.n_params = len(bt), sum(p.numel() for p in ps)
+            plan.n_blocks, plan.n_params, plan.n_groups = len(bt), sum(p.numel() for p in ps), len(steps)
             if ps:
                 capturing = torch.cuda.is_current_stream_capturing()
-                t_tab, t_blk = torch.tensor(rows, dtype=torch.int64), torch.tensor([bt, bc], dtype=torch.int32)
-                st = plan.stage(t_tab.shape, t_blk.shape, capturing)
-                st[0].copy_(t_tab)
-                st[1].copy_(t_blk)
-                if plan.tables is None or plan.tables.shape != t_tab.shape or plan.blk.shape != t_blk.shape:
-                    plan.tables = torch.empty(t_tab.shape, dtype=torch.int64, device=dev)
-                    plan.blk = torch.empty(t_blk.shape, dtype=torch.int32, device=dev)
+                T = len(ps)
+                # one int64 table: 7 rows of T entries, the distinct step-counter addresses, then (as raw bits) the
+                # float hyper-parameters and the int32 block map -- a single upload
+                t_tab = torch.tensor(rows, dtype=torch.int64).reshape(-1)
+                t_steps = torch.tensor(steps, dtype=torch.int64)
+                t_hyper = torch.tensor(hyper, dtype=torch.float32).reshape(-1)
+                t_blk = torch.tensor([bt, bc], dtype=torch.int32).reshape(-1)
+                pad = lambda n: (n + 1) // 2 * 2  # noqa: E731  (int32 / fp32 words -> whole int64 words)
+                host = torch.zeros(t_tab.numel() + t_steps.numel() + pad(t_hyper.numel()) // 2 + pad(t_blk.numel()) // 2,
+                                   dtype=torch.int64)
+                o1 = t_tab.numel()
+                o2 = o1 + t_steps.numel()
+                o3 = o2 + pad(t_hyper.numel()) // 2
+                host[:o1] = t_tab
+                host[o1:o2] = t_steps
+                host[o2:o3].view(torch.float32)[:t_hyper.numel()] = t_hyper
+                host[o3:].view(torch.int32)[:t_blk.numel()] = t_blk
+                st = plan.stage(host.shape, (1,), capturing)
+                st[0].copy_(host)
+                if plan.tables is None or plan.tables.shape != host.shape:
+                    plan.tables = torch.empty(host.shape, dtype=torch.int64, device=dev)
                 plan.tables.copy_(st[0], non_blocking=True)
-                plan.blk.copy_(st[1], non_blocking=True)
                 if not capturing:
                     st[2] = torch.cuda.Event()
                     st[2].record(torch.cuda.current_stream(dev))
+                plan.offsets = (T, o1, o2, o3)
             plan.sig = sig
             plan.keep = [g for p, g in zip(ps, grads) if g is not p.grad]  # contiguous copies must outlive the launch
         return plan, ps
@@ -168,30 +196,28 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.load()
-        capturing = None
+        live = []
         for gi, group in enumerate(self.param_groups):
             first = next((p for p in group["params"] if p.grad is not None), None)
             if first is None:
                 continue
             if not first.is_cuda:
                 raise RuntimeError("FusedAdam runs on contiguous fp32 CUDA parameters only (there is no CPU fallback)")
-            if capturing is None:
-                capturing = torch.cuda.is_current_stream_capturing()
-            gs = self._group_state(gi, group, first.device)
-            if not capturing:
-                self.sync_lr()
-            plan, ps = self._plan(gi, group, gs)
-            if not ps:
-                continue
-            tab, blk = plan.tables, plan.blk
-            T = tab.shape[1]
-            base, es = tab.data_ptr(), 8 * T
-            b1, b2 = group["betas"]
-            stream = ctypes.c_void_p(torch.cuda.current_stream(first.device).cuda_stream)
-            _lib.check(lib.sug_adam_f32(ctypes.c_void_p(base), ctypes.c_void_p(base + es), ctypes.c_void_p(base + 2 * es),
-                                        ctypes.c_void_p(base + 3 * es), ctypes.c_void_p(base + 4 * es),
-                                        ctypes.c_void_p(blk.data_ptr()), ctypes.c_void_p(blk.data_ptr() + 4 * plan.n_blocks),
-                                        plan.n_blocks, plan.n_params, ctypes.c_void_p(gs["step"].data_ptr()),
-                                        ctypes.c_void_p(gs["lr"].data_ptr()), float(b1), float(b2), float(group["eps"]),
-                                        float(group["weight_decay"]), stream), "sug_adam_f32")
+            live.append((gi, group, self._group_state(gi, group, first.device)))
+        if not live:
+            return loss
+        dev = next(p for p in live[0][1]["params"] if p.grad is not None).device
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
+        plan, ps = self._plan_all(live)
+        if not ps:
+            return loss
+        T, o1, o2, o3 = plan.offsets
+        base = plan.tables.data_ptr()
+        row = lambda r: ctypes.c_void_p(base + 8 * T * r)  # noqa: E731
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.sug_adam_multi_f32(row(0), row(1), row(2), row(3), row(4), row(5), row(6), ctypes.c_void_p(base + 8 * o2),
+                                          ctypes.c_void_p(base + 8 * o3), ctypes.c_void_p(base + 8 * o3 + 4 * plan.n_blocks),
+                                          plan.n_blocks, plan.n_params, ctypes.c_void_p(base + 8 * o1), plan.n_groups, stream),
+                   "sug_adam_multi_f32")
         return loss
