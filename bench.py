@@ -121,14 +121,14 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-def workload_config(B, world, mmd_scope="local", mode="cuda_graph", shared_trunk=False, nccl_in_graph=False):
-    """The `config` object of BOTH arms (ours and --impl reference): BASELINE.json configs[1] / [2]."""
+def workload_config(B, world, mmd_scope="local", shared_trunk=False):
+    """The `config` object -- IDENTICAL for both arms (ours and --impl reference) given the same command line:
+    BASELINE.json configs[1] (N = 1) / configs[2] (N > 1).  How an arm executes it is in the line's `execution` key."""
     return {"workload": "SUG DG train step: Net_MDA(DGCNN, k=20) x4 forwards + backward + 3 Adam, "
                         "CE(2 heads x 2 sub-domains) + GEO/SEM soft-MMD with SDA weights "
                         "(DG_unified_loss_onedataset_shapenet.yaml) = BASELINE.json configs[1]",
             "clouds_per_step_per_gpu": 2 * B, "batch_per_subdomain": B, "points": N_POINTS, "k": 20,
-            "classes": 10, "parallelism": f"dp{world}", "mmd_scope": mmd_scope, "execution": mode,
-            "shared_trunk": bool(shared_trunk), "nccl_in_graph": bool(nccl_in_graph),
+            "classes": 10, "parallelism": f"dp{world}", "mmd_scope": mmd_scope, "shared_trunk": bool(shared_trunk),
             "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -200,12 +200,12 @@ def run_reference(args, rank, emit):
     ts = [step() for _ in range(args.steps)]
     sec = sum(ts) / len(ts)
     val = 2 * bs / sec
-    cfg = workload_config(B_PER_GPU, 1, mode="cpu_eager")
-    cfg["parallelism"] = "cpu"
-    cfg["sample_batch_per_subdomain"] = bs
+    cfg = workload_config(args.batch, max(1, args.gpus), args.mmd_scope, args.share_trunk)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "execution": {"mode": "cpu_eager", "host_threads": step.threads, "sample_batch_per_subdomain": bs,
+                          "note": "one process on rank 0's host cores whatever --gpus says"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": step.threads, "kind": "port",
                              "sample": f"{args.steps} timed + {args.warmup} warm-up SUG steps at {bs}+{bs} clouds x {N_POINTS} pts "
                                        f"(a bounded sample of the 64+64 step: same network, losses, backward, Adam), "
@@ -540,7 +540,8 @@ def _main(args, rank, emit):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(B, world, args.mmd_scope, mode, args.share_trunk, nccl_in_graph),
+            "config": workload_config(B, world, args.mmd_scope, args.share_trunk),
+            "execution": {"mode": mode, "nccl_in_graph": bool(nccl_in_graph), "grad_allreduce_overlap": bool(nccl_in_graph and not args.no_overlap)},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},

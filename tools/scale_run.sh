@@ -20,7 +20,7 @@ for s in ("local", "global"):
     d = rd("gpurun_out/scale_n${N}_%s.log" % s)
     if d and b:
         print("N=${N}", s, round(d["ms_per_step"], 3), "ms", round(d["value"], 1), "clouds/s  efficiency vs same-box N=1:", round(d["value"] / (${N} * b["value"]), 4),
-              "in_sync", d.get("replicas_in_sync"), d["config"]["execution"], "e2e", round(d["e2e"]["value"], 1))
+              "in_sync", d.get("replicas_in_sync"), d["execution"]["mode"], "e2e", round(d["e2e"]["value"], 1))
     else:
         print("N=${N}", s, "no line")
 PY
