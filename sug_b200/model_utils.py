@@ -14,6 +14,18 @@ from . import ops
 from . import point_utils
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One auxiliary stream per device for work that overlaps the encoder trunk (adapt_layer_off.prefetch_indices)."""
+    key = torch.device(device).index
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 class conv_2d(nn.Module):
     """model_utils.py:8-32: Conv2d(kernel) -> BatchNorm2d -> ReLU | Tanh | LeakyReLU(0.01)."""
 
@@ -149,17 +161,43 @@ class adapt_layer_off(nn.Module):
         out_pm, node_pm, off_pm = self.forward_pm(fea.transpose(1, 2), input_loc)
         return out_pm.transpose(1, 2).unsqueeze(3), node_pm.transpose(1, 2).unsqueeze(3), off_pm.transpose(1, 2)
 
-    def forward_pm(self, fea, input_loc):
+    def prefetch_indices(self, input_loc):
+        """FPS (64 sequential rounds on 64 CTAs: latency-, not throughput-bound) and the ball query depend on the raw
+        cloud only, so they are issued on a SIDE STREAM as soon as the cloud is known and run next to the first two
+        EdgeConv layers of the encoder (fork / join edges when the step is captured into a CUDA graph).  Returns a
+        handle for ``forward_pm(..., pre=handle)``.  The FPS start is drawn here, i.e. still once per forward and in the
+        same order as the reference's RNG consumption (point_utils.py:17)."""
+        ops._need_cuda(input_loc)
+        main = torch.cuda.current_stream(input_loc.device)
+        side = _side_stream(input_loc.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            B = input_loc.shape[0]
+            loc = input_loc.transpose(1, 2)
+            bi = torch.arange(B, device=input_loc.device).view(B, 1)
+            fidx = point_utils.farthest_point_sample(input_loc, self.num_node)
+            f_loc = loc[bi, fidx]
+            gidx = point_utils.query_ball_point(0.3, 64, input_loc, f_loc.transpose(1, 2))
+        for t in (fidx, f_loc, gidx):
+            t.record_stream(main)
+        return fidx, f_loc, gidx, side
+
+    def forward_pm(self, fea, input_loc, pre=None):
         """Point-major core.  fea [B,N,C], input_loc [B,3,N] ->
         (cat(fea, interpolated) [B,N,2C], node_fea [B,S,C], node_offset [B,S,3]).
-        ``input_loc`` is the raw cloud in every reference model; no gradient is propagated to it."""
+        ``input_loc`` is the raw cloud in every reference model; no gradient is propagated to it.
+        ``pre``: the handle of ``prefetch_indices`` (FPS + ball query already running on a side stream)."""
         B, N, C = fea.shape
         S = self.num_node
         loc = input_loc.transpose(1, 2)  # [B,N,3] view
-        bi = torch.arange(B, device=fea.device).view(B, 1)
-        fidx = point_utils.farthest_point_sample(input_loc, S)                        # [B,S]
-        f_loc = loc[bi, fidx]                                                           # [B,S,3]
-        gidx = point_utils.query_ball_point(0.3, 64, input_loc, f_loc.transpose(1, 2))  # [B,S,64]
+        if pre is not None:
+            fidx, f_loc, gidx, side = pre
+            torch.cuda.current_stream(fea.device).wait_stream(side)
+        else:
+            bi = torch.arange(B, device=fea.device).view(B, 1)
+            fidx = point_utils.farthest_point_sample(input_loc, S)                        # [B,S]
+            f_loc = loc[bi, fidx]                                                           # [B,S,3]
+            gidx = point_utils.query_ball_point(0.3, 64, input_loc, f_loc.transpose(1, 2))  # [B,S,64]
         # pred_offset is a bias-free 1x1 conv, i.e. linear: W (fea[g] - fea[f]) = (W fea)[g] - (W fea)[f],
         # so the 64 -> 3 map runs once per point and only 3-vectors are gathered (model_utils.py:112-113)
         h = ops.linear(fea, self.pred_offset[0].weight)                                # [B,N,3]
