@@ -14,18 +14,6 @@ from . import ops
 from . import point_utils
 
 
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device):
-    """One auxiliary stream per device for work that overlaps the encoder trunk (adapt_layer_off.prefetch_indices)."""
-    key = torch.device(device).index
-    st = _SIDE_STREAMS.get(key)
-    if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-    return st
-
-
 class conv_2d(nn.Module):
     """model_utils.py:8-32: Conv2d(kernel) -> BatchNorm2d -> ReLU | Tanh | LeakyReLU(0.01)."""
 
@@ -169,7 +157,7 @@ class adapt_layer_off(nn.Module):
         same order as the reference's RNG consumption (point_utils.py:17)."""
         ops._need_cuda(input_loc)
         main = torch.cuda.current_stream(input_loc.device)
-        side = _side_stream(input_loc.device)
+        side = ops._side_stream(input_loc.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             B = input_loc.shape[0]
@@ -204,11 +192,26 @@ class adapt_layer_off(nn.Module):
         node_offset = ops.node_offset(h, input_loc, fidx, gidx)                         # [B,S,3] (lines 107-117, fused)
         node_loc = f_loc + node_offset
         node_loc_cm = node_loc.transpose(1, 2)                                          # [B,3,S]
-        gidx2 = ops.knn_query(input_loc, node_loc_cm, 64, ordered=False)               # [B,S,64] (a set)
-        residual_fea = self.residual.forward_pm(fea)                                    # [B,N,C]
+        if pre is not None:
+            # the 64-NN grouping and the 3-NN of the moved nodes are index builders (no autograd) that need the node
+            # positions only: on the side stream, next to the residual conv block of the main stream
+            main = torch.cuda.current_stream(fea.device)
+            side = pre[3]
+            nl = node_loc_cm.detach()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                gidx2 = ops.knn_query(input_loc, nl, 64, ordered=False)                 # [B,S,64] (a set)
+                idx3 = ops.three_nn(input_loc, nl, 3)                                   # [B,N,3] int32
+            gidx2.record_stream(main)
+            idx3.record_stream(main)
+            residual_fea = self.residual.forward_pm(fea)                                # [B,N,C]
+            main.wait_stream(side)
+        else:
+            gidx2 = ops.knn_query(input_loc, node_loc_cm, 64, ordered=False)           # [B,S,64] (a set)
+            residual_fea = self.residual.forward_pm(fea)                                # [B,N,C]
+            idx3 = ops.three_nn(input_loc, node_loc_cm, 3)                              # [B,N,3] int32
         node_fea = ops.group_max(residual_fea, gidx2)                                   # [B,S,C]
         # 3-NN inverse-squared-distance interpolation back to the points (point_utils.py:134-165)
-        idx3 = ops.three_nn(input_loc, node_loc_cm, 3)                                  # [B,N,3] int32
         weight = ops.interp_weights(input_loc, node_loc, idx3)                          # [B,N,3]
         interp = ops.interpolate(node_fea, idx3, weight)                                # [B,N,C]
         return torch.cat((fea, interp), dim=2), node_fea, node_offset

@@ -39,6 +39,19 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
+_SIDE = {}
+
+
+def _side_stream(device):
+    """One auxiliary stream per device for latency-bound index kernels that overlap the main stream's work
+    (adapt_layer_off.prefetch_indices / forward_pm)."""
+    key = torch.device(device).index
+    st = _SIDE.get(key)
+    if st is None:
+        st = _SIDE[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 def _rows(x: torch.Tensor, vec: bool = False) -> torch.Tensor:
     """[B,N,C] view whose (b,n) rows have one uniform stride and unit channel stride
     (``vec``: additionally 16-byte aligned rows for float4 access)."""
