@@ -65,6 +65,8 @@ int sug_knn_reverse(const int32_t* idx, int B, int N, int k, int32_t* rev_ptr, i
  * training == 0: running statistics; ext, arg, ssum, save_mean_invstd may be NULL (ab is scratch).
  * ------------------------------------------------------------------------------------------- */
 size_t sug_edgeconv_ws_bytes(int B, int N, int C, int Cout, int k);
+/* (training != 0: running_mean / running_var may be NULL -- the momentum update is then left to the caller, who finds
+ * the batch mean / invstd in save_mean_invstd; same for sug_mlp_pool_fwd and sug_linear_bn_act_fwd) */
 int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx, const float* w,
                      const float* gamma, const float* beta, float* running_mean, float* running_var,
                      int B, int N, int C, int Cout, int k, float eps, float momentum, float slope,

@@ -111,9 +111,7 @@ class DGCNN(nn.Module):
         return x1, x2
 
     def _tail(self, x_cat):
-        bn = self.bn5
-        if self.training and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        bn = ops.bn_tick(self.bn5, self.training)
         return ops.mlp_bn_act_pool(x_cat, self.conv5.weight, None, bn.weight, bn.bias, bn.running_mean,
                                    bn.running_var, self.training, 0.2, ops.POOL_MAX_AVG, bn.eps, bn.momentum)
 

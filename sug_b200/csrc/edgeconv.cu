@@ -884,7 +884,7 @@ extern "C" int sug_edgeconv_fwd(const float* x, int64_t ldx, const int32_t* idx,
   SUG_TRY(edge_check(B, N, C, Cout, k));
   SUG_CHECK_ARG(x && idx && w && gamma && beta && out && ab, "edgeconv_fwd: null pointer");
   SUG_CHECK_ARG(ldo % 4 == 0 && ((uintptr_t)out % 16) == 0, "edgeconv_fwd: out must be 16B aligned with ldo %% 4 == 0");
-  SUG_CHECK_ARG(running_mean && running_var, "edgeconv_fwd: running statistics required");
+  SUG_CHECK_ARG(training || (running_mean && running_var), "edgeconv_fwd: eval mode needs the running statistics");
   if (training) SUG_CHECK_ARG(ext && arg && ssum && save_mean_invstd, "edgeconv_fwd: training needs ext/arg/ssum/save");
   const long long P = (long long)B * N;
   Workspace W(ws, ws_bytes);

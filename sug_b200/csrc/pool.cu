@@ -387,7 +387,8 @@ extern "C" int sug_linear_bn_act_fwd(const float* x, int64_t ldx, const float* w
                                      float* out, int64_t ldo, float* save_mean_invstd, void* ws, size_t ws_bytes,
                                      sug_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  SUG_CHECK_ARG(x && w && gamma && beta && running_mean && running_var && y && out, "linear_bn_act_fwd: null pointer");
+  SUG_CHECK_ARG(x && w && gamma && beta && y && out, "linear_bn_act_fwd: null pointer");
+  SUG_CHECK_ARG(training || (running_mean && running_var), "linear_bn_act_fwd: eval mode needs the running statistics");
   SUG_CHECK_ARG(P > 0 && Cin > 0 && Cout > 0 && Cout % 4 == 0 && ldo % 4 == 0, "linear_bn_act_fwd: bad shape");
   Workspace W(ws, ws_bytes);
   double* sums = W.take<double>(2 * (size_t)Cout);
@@ -467,7 +468,8 @@ extern "C" int sug_mlp_pool_fwd(const float* x, int64_t ldx, const float* w, con
                                 float* out, int32_t* argext, float* save_mean_invstd, void* ws, size_t ws_bytes,
                                 sug_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  SUG_CHECK_ARG(x && w && gamma && beta && running_mean && running_var && y && out, "mlp_pool_fwd: null pointer");
+  SUG_CHECK_ARG(x && w && gamma && beta && y && out, "mlp_pool_fwd: null pointer");
+  SUG_CHECK_ARG(training || (running_mean && running_var), "mlp_pool_fwd: eval mode needs the running statistics");
   SUG_CHECK_ARG(B > 0 && N > 0 && Cin > 0 && Cout > 0 && Cout % 4 == 0, "mlp_pool_fwd: bad shape");
   SUG_CHECK_ARG(pool == SUG_POOL_MAX || pool == SUG_POOL_MAX_AVG, "mlp_pool_fwd: bad pool mode %d", pool);
   if (training) SUG_CHECK_ARG(argext && save_mean_invstd, "mlp_pool_fwd: training needs argext/save");

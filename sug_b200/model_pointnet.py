@@ -80,9 +80,7 @@ class DGCNN(nn.Module):
         x2 = self.conv2.edgeconv(x1, ops.knn_pm(x1, k))
         x3 = self.conv3.edgeconv(x2, ops.knn_pm(x2, k))
         x4 = self.conv4.edgeconv(x3, ops.knn_pm(x3, k))
-        bn = self.bn5
-        if self.training and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        bn = ops.bn_tick(self.bn5, self.training)
         feat = ops.mlp_bn_act_pool(torch.cat((x1, x2, x3, x4), dim=2), self.conv5.weight, None, bn.weight, bn.bias,
                                    bn.running_mean, bn.running_var, self.training, 0.2, ops.POOL_MAX_AVG, bn.eps,
                                    bn.momentum)

@@ -51,10 +51,7 @@ class conv_2d(nn.Module):
 
     # ---- fused fast paths (point-major tensors) -------------------------------------------------
     def _bn_tick(self):
-        bn = self.conv[1]
-        if self.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
-        return bn
+        return ops.bn_tick(self.conv[1], self.training)
 
     def _slope(self):
         act = self.conv[2]

@@ -43,13 +43,81 @@ _SIDE = {}
 
 
 def _side_stream(device):
-    """One auxiliary stream per device for latency-bound index kernels that overlap the main stream's work
+    """One auxiliary stream per (device, current stream) for latency-bound index kernels that overlap the main stream's work
     (adapt_layer_off.prefetch_indices / forward_pm)."""
-    key = torch.device(device).index
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
     st = _SIDE.get(key)
     if st is None:
         st = _SIDE[key] = torch.cuda.Stream(device=device)
     return st
+
+
+class BNRecorder:
+    """Deferred BatchNorm side effects.  While a recorder is installed (``ops.BN_RECORDER``) the fused ops of this module
+    do NOT touch running_mean / running_var / num_batches_tracked; they record (buffers, batch statistics) per pass
+    instead, and ``apply()`` performs the momentum updates afterwards, pass by pass in the recorded order.  That is what
+    lets two encoder passes of one step run CONCURRENTLY on two streams (step.sug_losses): the exponential moving
+    average is order dependent (first the source pass, then the target pass, train_dg_single_gpu.py:260-264), so the
+    updates cannot race -- the batch statistics, the outputs and the gradients do not depend on the running buffers."""
+
+    def __init__(self):
+        self.passes = {}
+        self.current = 0
+
+    def _p(self):
+        return self.passes.setdefault(self.current, {"bn": [], "nbt": []})
+
+    def add(self, running_mean, running_var, save, count, momentum, eps):
+        self._p()["bn"].append((running_mean, running_var, save, float(count), float(momentum), float(eps)))
+
+    def tick(self, nbt):
+        self._p()["nbt"].append(nbt)
+
+    @torch.no_grad()
+    def apply(self):
+        for key in sorted(self.passes):
+            ent = self.passes[key]
+            if ent["nbt"]:
+                torch._foreach_add_(ent["nbt"], 1)
+            if not ent["bn"]:
+                continue
+            rms = [e[0] for e in ent["bn"]]
+            rvs = [e[1] for e in ent["bn"]]
+            C = [e[0].numel() for e in ent["bn"]]
+            means = [e[2][:c] for e, c in zip(ent["bn"], C)]
+            invstds = [e[2][c:] for e, c in zip(ent["bn"], C)]
+            mom = [e[4] for e in ent["bn"]]
+            # biased batch variance back from invstd = 1 / sqrt(var + eps); unbiased for the running estimate
+            var = torch._foreach_pow(invstds, -2.0)
+            torch._foreach_sub_(var, [e[5] for e in ent["bn"]])
+            torch._foreach_clamp_min_(var, 0.0)
+            torch._foreach_mul_(var, [m * (e[3] / (e[3] - 1.0) if e[3] > 1.0 else 1.0) for e, m in zip(ent["bn"], mom)])
+            torch._foreach_mul_(rms, [1.0 - m for m in mom])
+            torch._foreach_mul_(rvs, [1.0 - m for m in mom])
+            torch._foreach_add_(rms, torch._foreach_mul(means, mom))
+            torch._foreach_add_(rvs, var)
+        self.passes = {}
+
+
+BN_RECORDER = None
+
+
+def bn_tick(bn, training):
+    """num_batches_tracked += 1 like nn.BatchNorm does in training mode -- deferred when a recorder is installed."""
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        if BN_RECORDER is not None:
+            BN_RECORDER.tick(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked.add_(1)
+    return bn
+
+
+def _running(running_mean, running_var, save, count, momentum, eps, training):
+    """The running buffers a fused op should update itself: none while a recorder defers the update."""
+    if training and BN_RECORDER is not None and running_mean is not None:
+        BN_RECORDER.add(running_mean, running_var, save, count, momentum, eps)
+        return None, None
+    return running_mean, running_var
 
 
 def _rows(x: torch.Tensor, vec: bool = False) -> torch.Tensor:
@@ -138,6 +206,7 @@ class _EdgeConvFn(torch.autograd.Function):
             save = torch.empty(2 * Cout, dtype=torch.float32, device=dev)
         else:
             ext = ssum = arg = save = None
+        running_mean, running_var = _running(running_mean, running_var, save, P * k, momentum, eps, training)
         with torch.cuda.device(dev):
             _lib.check(lib.sug_edgeconv_fwd(_ptr(x), x.stride(1), _ptr(idx), _ptr(w2), _ptr(gamma.detach()),
                                             _ptr(beta.detach()), _ptr(running_mean), _ptr(running_var), B, N, C, Cout,
@@ -252,6 +321,7 @@ class _MlpPoolFn(torch.autograd.Function):
         ws = _workspace(lib.sug_mlp_pool_ws_bytes(B, N, Cin, Cout), dev)
         argext = torch.empty(B, Cout, dtype=torch.int32, device=dev) if training else None
         save = torch.empty(2 * Cout, dtype=torch.float32, device=dev) if training else None
+        running_mean, running_var = _running(running_mean, running_var, save, B * N, momentum, eps, training)
         with torch.cuda.device(dev):
             _lib.check(lib.sug_mlp_pool_fwd(_ptr(x), x.stride(1), _ptr(w2), _ptr(None if bias is None else bias.detach()),
                                             _ptr(gamma.detach()), _ptr(beta.detach()), _ptr(running_mean),
@@ -318,6 +388,7 @@ class _LinearBnActFn(torch.autograd.Function):
         save = torch.empty(2 * Cout, dtype=torch.float32, device=dev) if training else None
         lib = _lib.load()
         ws = _workspace(32 * Cout + 4096, dev)
+        running_mean, running_var = _running(running_mean, running_var, save, P, momentum, eps, training)
         with torch.cuda.device(dev):
             _lib.check(lib.sug_linear_bn_act_fwd(_ptr(x2), x2.stride(0), _ptr(w2), _ptr(None if bias is None else bias.detach()),
                                                  _ptr(gamma.detach()), _ptr(beta.detach()), _ptr(running_mean),

@@ -6,6 +6,8 @@ reference trainer itself runs unchanged through ``sug_b200.compat``.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import mmd
@@ -20,12 +22,74 @@ SUG_CFG = {  # METHODS section of DG_unified_loss_onedataset_shapenet.yaml
 OPT_CFG = {"LR": 1e-4, "LR_SCALER": 1.0, "WEIGHT_DECAY": 5e-4}  # OPTIMIZATION section
 
 
+_PAIR_STREAMS = {}
+
+
+class ConcurrentPasses:
+    """Runs the two encoder passes of a step (source batch, target batch) CONCURRENTLY on two CUDA streams.
+
+    The two passes share nothing but the weights (read-only) and the BatchNorm running buffers; the latter are updated
+    through ``ops.BNRecorder`` AFTER both passes, source first, exactly in the reference's order
+    (train_dg_single_gpu.py:260-264, 309-310), so losses, gradients and buffers are what the sequential execution
+    produces.  What the concurrency buys: the step's kernels come in 3.46 waves of CTAs (64 clouds on 148 SMs) and many
+    of them are latency-bound (FPS, counting sorts, index kernels, small GEMMs): a second stream fills the tails.  The
+    backward follows automatically (autograd runs every node on the stream of its forward).  Captured into the step's
+    CUDA graph as fork / join edges.  Off for CPU tensors, eval mode and the opt-in shared trunk."""
+
+    def __init__(self, model, device):
+        from . import ops
+        self.ops = ops
+        self.dev = torch.device(device)
+        self.on = (self.dev.type == "cuda" and model.training and ENABLE_CONCURRENT_PASSES
+                   and not getattr(getattr(model, "g", None), "share_trunk", False))
+        if self.on:
+            key = (self.dev.index, torch.cuda.current_stream(self.dev).cuda_stream)
+            if key not in _PAIR_STREAMS:
+                _PAIR_STREAMS[key] = (torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev))
+            self.streams = _PAIR_STREAMS[key]
+            self.rec = ops.BNRecorder()
+
+    def __enter__(self):
+        if self.on:
+            self.main = torch.cuda.current_stream(self.dev)
+            for st in self.streams:
+                st.wait_stream(self.main)
+            self.prev = self.ops.BN_RECORDER
+            self.ops.BN_RECORDER = self.rec
+        return self
+
+    def run(self, i, fn):
+        if not self.on:
+            return fn()
+        self.rec.current = i
+        with torch.cuda.stream(self.streams[i]):
+            out = fn()
+        for t in (out if isinstance(out, (tuple, list)) else (out,)):
+            if isinstance(t, torch.Tensor):
+                t.record_stream(self.main)
+        return out
+
+    def __exit__(self, et, ev, tb):
+        if self.on:
+            self.ops.BN_RECORDER = self.prev
+            for st in self.streams:
+                self.main.wait_stream(st)
+            if et is None:
+                self.rec.apply()
+        return False
+
+
+ENABLE_CONCURRENT_PASSES = os.environ.get("SUG_B200_CONCURRENT_PASSES", "1") == "1"
+
+
 def sug_losses(model, data, label, data_t, label_t, criterion, cfg=SUG_CFG, mmd_fn=mmd.mmd_cal):
     """train_dg_single_gpu.py:260-324: four Net_MDA forwards, class-weighted CE on both heads and
     both sub-domains (target logits are scored against the SOURCE labels, lines 287-288), the
-    geometric MMD on the node features and the semantic MMD on both heads."""
-    pred_s1, pred_s2, sem_s1, sem_s2 = model(data, semantic_adaption=True)
-    pred_t1, pred_t2, sem_t1, sem_t2 = model(data_t, semantic_adaption=True)
+    geometric MMD on the node features and the semantic MMD on both heads.  The source and the target pass of each
+    pair run concurrently on two streams (``ConcurrentPasses``: same results, BatchNorm buffers updated in order)."""
+    with ConcurrentPasses(model, data.device) as cp:
+        pred_s1, pred_s2, sem_s1, sem_s2 = cp.run(0, lambda: model(data, semantic_adaption=True))
+        pred_t1, pred_t2, sem_t1, sem_t2 = cp.run(1, lambda: model(data_t, semantic_adaption=True))
     loss_s = 0.5 * criterion(pred_s1, label) + 0.5 * criterion(pred_s2, label)
     if cfg["TARGET_LOSS"] > 0:
         loss_t = 0.5 * criterion(pred_t1, label) + 0.5 * criterion(pred_t2, label)
@@ -33,8 +97,9 @@ def sug_losses(model, data, label, data_t, label_t, criterion, cfg=SUG_CFG, mmd_
     else:
         loss = cfg["SRC_LOSS_WEIGHT"] * loss_s
     loss_cls = cfg["CLS_WEIGHT"] * loss
-    feat_node_s = model(data, node_adaptation_s=True)
-    feat_node_t = model(data_t, node_adaptation_t=True)
+    with ConcurrentPasses(model, data.device) as cp:
+        feat_node_s = cp.run(0, lambda: model(data, node_adaptation_s=True))
+        feat_node_t = cp.run(1, lambda: model(data_t, node_adaptation_t=True))
     geo, sem = cfg["GEO_MMD"][0], cfg["SEM_MMD"][0]
     loss_geo = cfg["MMD_WEIGHT"] * geo["GEO_SCALE"] * mmd_fn(label, feat_node_s, label_t, feat_node_t, geo,
                                                              data_s=data, data_t=data_t)
