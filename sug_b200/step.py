@@ -45,8 +45,8 @@ class ConcurrentPasses:
         if self.on:
             key = (self.dev.index, torch.cuda.current_stream(self.dev).cuda_stream)
             if key not in _PAIR_STREAMS:
-                _PAIR_STREAMS[key] = (torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev))
-            self.streams = _PAIR_STREAMS[key]
+                _PAIR_STREAMS[key] = tuple(torch.cuda.Stream(device=self.dev) for _ in range(4))
+            self.streams = _PAIR_STREAMS[key][:max(1, min(4, N_CONCURRENT))]
             self.rec = ops.BNRecorder()
 
     def __enter__(self):
@@ -62,7 +62,7 @@ class ConcurrentPasses:
         if not self.on:
             return fn()
         self.rec.current = i
-        with torch.cuda.stream(self.streams[i]):
+        with torch.cuda.stream(self.streams[i % len(self.streams)]):
             out = fn()
         for t in (out if isinstance(out, (tuple, list)) else (out,)):
             if isinstance(t, torch.Tensor):
@@ -80,6 +80,7 @@ class ConcurrentPasses:
 
 
 ENABLE_CONCURRENT_PASSES = os.environ.get("SUG_B200_CONCURRENT_PASSES", "1") == "1"
+N_CONCURRENT = int(os.environ.get("SUG_B200_N_CONCURRENT", "4"))
 
 
 def sug_losses(model, data, label, data_t, label_t, criterion, cfg=SUG_CFG, mmd_fn=mmd.mmd_cal):
@@ -87,9 +88,12 @@ def sug_losses(model, data, label, data_t, label_t, criterion, cfg=SUG_CFG, mmd_
     both sub-domains (target logits are scored against the SOURCE labels, lines 287-288), the
     geometric MMD on the node features and the semantic MMD on both heads.  The source and the target pass of each
     pair run concurrently on two streams (``ConcurrentPasses``: same results, BatchNorm buffers updated in order)."""
+    # all four forwards are independent of each other (the node passes recompute the encoder): four streams
     with ConcurrentPasses(model, data.device) as cp:
         pred_s1, pred_s2, sem_s1, sem_s2 = cp.run(0, lambda: model(data, semantic_adaption=True))
         pred_t1, pred_t2, sem_t1, sem_t2 = cp.run(1, lambda: model(data_t, semantic_adaption=True))
+        feat_node_s = cp.run(2, lambda: model(data, node_adaptation_s=True))
+        feat_node_t = cp.run(3, lambda: model(data_t, node_adaptation_t=True))
     loss_s = 0.5 * criterion(pred_s1, label) + 0.5 * criterion(pred_s2, label)
     if cfg["TARGET_LOSS"] > 0:
         loss_t = 0.5 * criterion(pred_t1, label) + 0.5 * criterion(pred_t2, label)
@@ -97,9 +101,6 @@ def sug_losses(model, data, label, data_t, label_t, criterion, cfg=SUG_CFG, mmd_
     else:
         loss = cfg["SRC_LOSS_WEIGHT"] * loss_s
     loss_cls = cfg["CLS_WEIGHT"] * loss
-    with ConcurrentPasses(model, data.device) as cp:
-        feat_node_s = cp.run(0, lambda: model(data, node_adaptation_s=True))
-        feat_node_t = cp.run(1, lambda: model(data_t, node_adaptation_t=True))
     geo, sem = cfg["GEO_MMD"][0], cfg["SEM_MMD"][0]
     loss_geo = cfg["MMD_WEIGHT"] * geo["GEO_SCALE"] * mmd_fn(label, feat_node_s, label_t, feat_node_t, geo,
                                                              data_s=data, data_t=data_t)
