@@ -22,6 +22,14 @@
 // of the tiles (the k-th best of a subset is still a valid bound) -- the ~2k + 12 survivors per row make the
 // rank-by-counting and the list prunes quadratically more expensive: 372 us against 168 us; candidate lo tiles
 // precomputed per call and loaded by TMA (a two-party TMA -> MMA ring without the split hop): 172 us, no gain.
+// More of the same series (all bit-exact, timed back to back with this version on one box, 181 us with the Python call
+// around it): a third selection group (576 threads, 96 registers, 16 slot maxima per thread) -- only the sweeps shrink
+// per thread, the per-block phases (sort, threshold exchange, rank) do not, and with as many groups as accumulators the
+// MMA of a group's next tile waits for that group: 213 us; 8-byte {key, id} list entries (one STS.64 per candidate,
+// 9 -> 7 instructions) with or without a predicated tail advance: 180 / 190 us; rank by compare + predicated add
+// (3 -> 2 instructions per pair): 179 us; 32-candidate chunks without register spills: 189 us.  A clock64 breakdown
+// of this kernel (profiles/r02_notes.md) shows why none of them pays: the selection warps spend their time in
+// dependency stalls (0.2 instructions per cycle each, two of them per scheduler), not in issue slots.
 // Two selection groups (4 warps each) alternate over the accumulator buffers, so a query row is served
 // by two threads (one per group) which exchange T, list sizes and lists through shared memory.
 // Key = (-|x_i|^2 + 2 x_i.x_j) - |x_j|^2, the reference's operation order.
