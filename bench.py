@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--dp-no-comm", action="store_true",
                     help="DIAGNOSTIC ONLY (the line is marked invalid): N independent replicas without the gradient "
                          "all-reduce, to separate communication cost from multi-process interference")
+    ap.add_argument("--no-serial-roofline", action="store_true",
+                    help="skip timed region 3 (single-stream replay that times the dominant kernel class alone)")
     ap.add_argument("--share-trunk", action="store_true",
                     help="NOT the headline configuration: let the second encoder pass on a batch reuse conv1/conv2 of the "
                          "first (DGCNN.share_trunk); the default times the four full forwards the reference runs")
@@ -455,6 +457,42 @@ def _main(args, rank, emit):
     ms_e2e = float(t.item())
     e2e_value = clouds_per_step * args.steps / (ms_e2e / 1e3)
 
+    # ---- timed region 3 (1 GPU): the same graphed step on ONE stream, for the roofline of the dominant kernel ----------
+    # In regions 1 / 2 the four encoder passes share the SMs (up to four streams inside the graph), so an event pair
+    # around a launch measures the launch PLUS whatever the other streams ran in its window.  The roofline wants the
+    # kernel's own duration: replay the step once more with the concurrency switched off and time the launches there.
+    prof_serial, ms_serial = None, None
+    if graphed is not None and world == 1 and step.ENABLE_CONCURRENT_PASSES and not args.no_serial_roofline:
+        trace("timed region 3 (single-stream replay for the roofline)")
+        try:
+            step.ENABLE_CONCURRENT_PASSES = False
+            fps_flag, model.g.overlap_fps = model.g.overlap_fps, False
+            for o in opts:
+                o.zero_grad(set_to_none=True)
+            serial = step.GraphedTrainStep(model, opts, crit, B, N_POINTS, dev, mmd_fn=mmd_fn, grad_hook=hook)
+            serial.warm(*dev_batches[0])
+            _lib.prof_reset(mask=prof_mask)
+            serial.capture()
+            for i in range(3):
+                serial(*dev_batches[i % len(dev_batches)])
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(args.steps):
+                serial(*dev_batches[i % len(dev_batches)])
+            s1.record()
+            barrier()
+            ms_serial = s0.elapsed_time(s1) / args.steps
+            prof_serial = _lib.prof_collect()
+            del serial
+        except Exception as e:
+            print(f"[bench] single-stream replay failed ({type(e).__name__}: {e}); roofline from the concurrent replay",
+                  file=sys.stderr)
+            prof_serial = None
+        finally:
+            step.ENABLE_CONCURRENT_PASSES = True
+            model.g.overlap_fps = fps_flag
+
     trace("done timing")
     # ---- data parallel: every replica must hold the same weights after the timed steps ---------------------
     replicas_in_sync = None
@@ -479,6 +517,18 @@ def _main(args, rank, emit):
         # graph replays re-record the same event pairs: the totals are those of the LAST timed step
         d = dict(d, launches=d["timed"], flops=d["flops"], bytes=d["bytes"])
     per_launch_s = (d["ms"] / 1e3) / max(1, d["timed"])
+    step_ms_for_share = ms / args.steps if graphed is not None else ms
+    concurrent = None
+    if prof_serial is not None and prof_serial[dom]["timed"]:
+        # the dominant class as the concurrent replay saw it (kept for the record), then switch to the single-stream one
+        concurrent = {"avg_launch_us": per_launch_s * 1e6, "launches_timed": int(d["timed"]),
+                      "sum_of_launch_windows_over_step": d["ms"] / step_ms_for_share,
+                      "what": "event pairs around the same launches in timed region 1: four streams share the SMs, a "
+                              "window holds other streams' work too"}
+        ds = prof_serial[dom]
+        d = dict(ds, launches=ds["timed"])
+        per_launch_s = (d["ms"] / 1e3) / max(1, d["timed"])
+        step_ms_for_share = ms_serial
 
     # Every tensor-core kernel of this library is fp32-accurate 3xTF32 (hi/lo split, three kind::tf32 products per
     # algorithmic product: the parity gate is fp32), so its tensor roofline is a third of the dense TF32 rate -- measured
@@ -523,7 +573,13 @@ def _main(args, rank, emit):
     roof["traffic"] = traffic
     roof.update({"kernel": dom, "launches_timed": int(d["timed"]), "avg_launch_us": per_launch_s * 1e6,
                  "algorithmic_bytes_per_launch": bytes_pl, "algorithmic_flops_per_launch": flops_pl,
-                 "share_of_step": d["ms"] / (ms / args.steps if graphed is not None else ms)})
+                 "share_of_step": d["ms"] / step_ms_for_share})
+    if concurrent is not None:
+        roof["timed_in"] = ("single-stream replay of the same graphed step (timed region 3, %.3f ms per step): CUDA events "
+                            "on the launch stream around every launch of the class" % ms_serial)
+        roof["concurrent_replay"] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in concurrent.items()}
+    else:
+        roof["timed_in"] = "timed region 1: CUDA events on the launch stream around every launch of the class"
 
     # every kernel class of the step (the metric names the kNN / EdgeConv kernels, which are not the largest class):
     # launches, average device time and algorithmic work per launch from the instrumented eager step that precedes

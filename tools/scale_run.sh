@@ -3,7 +3,7 @@
 # (also runs --gpus 1 on the same box first, so that the efficiency has a same-box denominator).
 N=$1; shift
 mkdir -p gpurun_out
-python bench.py --gpus 1 --steps 30 --warmup 5 --no-cpu-baseline --no-torch-reference > gpurun_out/scale_n1_on${N}.log 2> gpurun_out/scale_n1_on${N}.err
+python bench.py --gpus 1 --steps 30 --warmup 5 --no-cpu-baseline --no-torch-reference --no-serial-roofline > gpurun_out/scale_n1_on${N}.log 2> gpurun_out/scale_n1_on${N}.err
 for scope in local global; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 \
       bench.py --gpus $N --steps 30 --warmup 5 --no-cpu-baseline --mmd-scope $scope "$@" > gpurun_out/scale_n${N}_${scope}.log 2> gpurun_out/scale_n${N}_${scope}.err
