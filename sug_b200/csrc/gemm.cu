@@ -113,9 +113,11 @@ int gemm_simt_f32(const float* a, int64_t sam, int64_t sak, const float* b, int6
   SUG_CHECK_ARG(a && b && c, "gemm: null operand");
   const int tm = cdiv(M, GBM), tn = cdiv(N, GBN);
   const long long tiles = (long long)tm * tn;
+  // few output tiles and a long reduction (the 128 x 128 Gram matrix of the MMD over 512 ... 4106 features, narrow
+  // weight gradients): split K until about two CTAs per SM are in flight, 64 k per CTA at least
   int splits = 1;
-  if (tiles < num_sms() && K >= 1024) {
-    splits = (int)min((long long)cdiv(K, 512), (2LL * num_sms() + tiles - 1) / tiles);
+  if (tiles < num_sms() && K >= 256) {
+    splits = (int)min((long long)cdiv(K, 64), (2LL * num_sms() + tiles - 1) / tiles);
     if (splits < 1) splits = 1;
   }
   int kchunk = cdiv(cdiv(K, splits), GBK) * GBK;

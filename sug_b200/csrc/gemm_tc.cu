@@ -253,6 +253,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t chunk_it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
       const int nt = t % p.tiles_n, mt = (t / p.tiles_n) % p.tiles_m;
+      // split-K: the partial sums are reduced into a zeroed C, the first k-range brings the bias along
+      const bool add_bias = p.bias != nullptr && t < p.tiles_n * p.tiles_m;
       const int ab = tile_it & 1;
       mbar_wait(&tfull[ab], (tile_it >> 1) & 1);
       tc_fence_after();
@@ -266,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + ab * BN + c * 32, v);
           tmem_ld_wait();
           const int col0 = nt * BN + c * 32;
-          if (p.bias != nullptr && p.epi == EPI_STORE) {
+          if (add_bias) {
 #pragma unroll
             for (int q = 0; q < 32; ++q)
               if (col0 + q < p.N) v[q] += __ldg(p.bias + col0 + q);
@@ -327,7 +329,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int q = 0; q < 32; ++q) {
               if (col0 + q < p.N) {
                 float o = v[q];
-                if (p.bias != nullptr && p.epi == EPI_STORE) o += __ldg(p.bias + col0 + q);
+                if (add_bias) o += __ldg(p.bias + col0 + q);
                 if (p.epi == EPI_ATOMIC) atomicAdd(crow + col0 + q, o);
                 else crow[col0 + q] = o;
               }
@@ -433,7 +435,7 @@ int gemm_tc_stats_f32(const float* a, int64_t lda, int a_mn, const float* b, int
   const int kb_total = cdiv(K, TBK);
   const long long tiles = (long long)args.tiles_m * args.tiles_n;
   int splits = 1;
-  if (tiles < num_sms() && kb_total >= 16 && bias == nullptr) {
+  if (tiles < num_sms() && kb_total >= 16) {
     splits = (int)min((long long)(kb_total / 8), (num_sms() + tiles - 1) / tiles);
     if (splits < 1) splits = 1;
   }
@@ -444,7 +446,6 @@ int gemm_tc_stats_f32(const float* a, int64_t lda, int a_mn, const float* b, int
   args.colsums = (colsums != nullptr && args.epi == EPI_STORE && c_tma) ? colsums : nullptr;
   if (fused != nullptr) *fused = args.colsums != nullptr;
   if (args.epi == EPI_ATOMIC) {
-    SUG_CHECK_ARG(bias == nullptr, "gemm_tc: bias with split-K is not supported");
     SUG_CUDA(cudaMemset2DAsync(c, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
   }
   const int grid = (int)min((long long)num_sms(), tiles * args.ksplits);

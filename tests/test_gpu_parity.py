@@ -1127,18 +1127,19 @@ def test_lidar_scale_inference(S):
 
 def test_graphed_eval_matches_eager(S):
     """step.GraphedEval: the eval forward as one CUDA graph returns what the eager forward returns --
-    model_pointnet.DGCNN (no RNG) bit for bit, Net_MDA('DGCNN') with the FPS start fed from the device buffer under
-    the same CPU RNG stream."""
+    model_pointnet.DGCNN (no RNG) up to the order of the fp32 additions (the batch-sized head GEMMs split K over the
+    SMs and reduce with atomics, so two runs of the SAME path differ in the last bit too), Net_MDA('DGCNN') with the
+    FPS start fed from the device buffer under the same CPU RNG stream."""
     x = O.synth_clouds(2, 2048, 77)[0].to(DEV)
     net = S.model_pointnet.DGCNN().to(DEV).eval()
     with torch.no_grad():
         ref = net(x)
     fwd = S.step.GraphedEval(net, x)
-    assert torch.equal(fwd(x), ref)
+    assert_close(fwd(x), ref, 1e-6, "graphed DGCNN logits")
     x2 = O.synth_clouds(2, 2048, 78)[0]
     with torch.no_grad():
         ref2 = net(x2.to(DEV))
-    assert torch.equal(fwd(x2.pin_memory()), ref2)
+    assert_close(fwd(x2.pin_memory()), ref2, 1e-6, "graphed DGCNN logits, second input")
     mda = _load(S.Model.Net_MDA("DGCNN"), "Net_MDA:DGCNN").eval()
     x3 = O.synth_clouds(3, 1024, 79)[0].to(DEV)
     g = S.step.GraphedEval(mda, x3, fps_points=1024)
