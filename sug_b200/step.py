@@ -75,8 +75,20 @@ class ConcurrentPasses:
             for st in self.streams:
                 self.main.wait_stream(st)
             if et is None:
-                self.rec.apply()
+                # the ~40 small multi-tensor launches of the deferred running-statistics updates go to a side stream:
+                # nothing of the step reads the running buffers, so they run next to the losses; join() waits for them
+                side = self.streams[-1]
+                side.wait_stream(self.main)
+                with torch.cuda.stream(side):
+                    self.rec.apply()
+                self.pending = side
         return False
+
+    def join(self):
+        """Makes the current stream wait for the deferred BatchNorm updates (call once, after the losses)."""
+        side, self.pending = getattr(self, "pending", None), None
+        if side is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(side)
 
 
 ENABLE_CONCURRENT_PASSES = os.environ.get("SUG_B200_CONCURRENT_PASSES", "1") == "1"
@@ -107,6 +119,7 @@ def sug_losses(model, data, label, data_t, label_t, criterion, cfg=SUG_CFG, mmd_
     l1 = sem["SEM_SCALE"] * mmd_fn(label, sem_s1, label_t, sem_t1, sem, data_s=pred_s1, data_t=pred_t1)
     l2 = sem["SEM_SCALE"] * mmd_fn(label, sem_s2, label_t, sem_t2, sem, data_s=pred_s2, data_t=pred_t2)
     loss_sem = cfg["MMD_WEIGHT"] * (0.5 * l1 + 0.5 * l2)
+    cp.join()
     return {"loss": loss_cls + loss_geo + loss_sem, "loss_cls": loss_cls, "loss_geo": loss_geo,
             "loss_sem": loss_sem, "pred_s1": pred_s1, "pred_t1": pred_t1}
 
