@@ -84,6 +84,29 @@ class ConcurrentPasses:
                 self.pending = side
         return False
 
+    def lanes(self, n):
+        """Up to ``n`` side streams forked from the current stream (None when the concurrency is off)."""
+        if not self.on or len(self.streams) < 2:
+            return None
+        main = torch.cuda.current_stream(self.dev)
+        lanes = [self.streams[i % (len(self.streams) - 1)] for i in range(n)]  # the last stream carries the BN updates
+        for st in set(lanes):
+            st.wait_stream(main)
+        return lanes
+
+    def lane(self, lanes, i):
+        import contextlib
+        return torch.cuda.stream(lanes[i]) if lanes else contextlib.nullcontext()
+
+    def merge(self, lanes, tensors):
+        """Joins the lanes into the current stream; ``tensors`` were produced on them."""
+        if lanes:
+            main = torch.cuda.current_stream(self.dev)
+            for st in set(lanes):
+                main.wait_stream(st)
+            for t in tensors:
+                t.record_stream(main)
+
     def join(self):
         """Makes the current stream wait for the deferred BatchNorm updates (call once, after the losses)."""
         side, self.pending = getattr(self, "pending", None), None
@@ -114,10 +137,17 @@ def sug_losses(model, data, label, data_t, label_t, criterion, cfg=SUG_CFG, mmd_
         loss = cfg["SRC_LOSS_WEIGHT"] * loss_s
     loss_cls = cfg["CLS_WEIGHT"] * loss
     geo, sem = cfg["GEO_MMD"][0], cfg["SEM_MMD"][0]
-    loss_geo = cfg["MMD_WEIGHT"] * geo["GEO_SCALE"] * mmd_fn(label, feat_node_s, label_t, feat_node_t, geo,
-                                                             data_s=data, data_t=data_t)
-    l1 = sem["SEM_SCALE"] * mmd_fn(label, sem_s1, label_t, sem_t1, sem, data_s=pred_s1, data_t=pred_t1)
-    l2 = sem["SEM_SCALE"] * mmd_fn(label, sem_s2, label_t, sem_t2, sem, data_s=pred_s2, data_t=pred_t2)
+    # the three MMD terms are independent chains of small kernels (weights, Gram matrix, kernel sums): on three streams
+    # when the passes ran concurrently (not with a collective inside mmd_fn: one communicator, one issue order)
+    lanes = cp.lanes(3) if mmd_fn is mmd.mmd_cal else None
+    with cp.lane(lanes, 0):
+        loss_geo = cfg["MMD_WEIGHT"] * geo["GEO_SCALE"] * mmd_fn(label, feat_node_s, label_t, feat_node_t, geo,
+                                                                 data_s=data, data_t=data_t)
+    with cp.lane(lanes, 1):
+        l1 = sem["SEM_SCALE"] * mmd_fn(label, sem_s1, label_t, sem_t1, sem, data_s=pred_s1, data_t=pred_t1)
+    with cp.lane(lanes, 2):
+        l2 = sem["SEM_SCALE"] * mmd_fn(label, sem_s2, label_t, sem_t2, sem, data_s=pred_s2, data_t=pred_t2)
+    cp.merge(lanes, (loss_geo, l1, l2))
     loss_sem = cfg["MMD_WEIGHT"] * (0.5 * l1 + 0.5 * l2)
     cp.join()
     return {"loss": loss_cls + loss_geo + loss_sem, "loss_cls": loss_cls, "loss_geo": loss_geo,
