@@ -121,21 +121,15 @@ N_CONCURRENT = int(os.environ.get("SUG_B200_N_CONCURRENT", "4"))
 def sug_losses(model, data, label, data_t, label_t, criterion, cfg=SUG_CFG, mmd_fn=mmd.mmd_cal):
     """train_dg_single_gpu.py:260-324: four Net_MDA forwards, class-weighted CE on both heads and
     both sub-domains (target logits are scored against the SOURCE labels, lines 287-288), the
-    geometric MMD on the node features and the semantic MMD on both heads.  The source and the target pass of each
-    pair run concurrently on two streams (``ConcurrentPasses``: same results, BatchNorm buffers updated in order)."""
+    geometric MMD on the node features and the semantic MMD on both heads.  The four passes run concurrently on up to
+    four streams (``ConcurrentPasses``: same results, BatchNorm buffers updated afterwards in the reference's order, on a
+    side stream), and so do the three MMD terms and the classification losses."""
     # all four forwards are independent of each other (the node passes recompute the encoder): four streams
     with ConcurrentPasses(model, data.device) as cp:
         pred_s1, pred_s2, sem_s1, sem_s2 = cp.run(0, lambda: model(data, semantic_adaption=True))
         pred_t1, pred_t2, sem_t1, sem_t2 = cp.run(1, lambda: model(data_t, semantic_adaption=True))
         feat_node_s = cp.run(2, lambda: model(data, node_adaptation_s=True))
         feat_node_t = cp.run(3, lambda: model(data_t, node_adaptation_t=True))
-    loss_s = 0.5 * criterion(pred_s1, label) + 0.5 * criterion(pred_s2, label)
-    if cfg["TARGET_LOSS"] > 0:
-        loss_t = 0.5 * criterion(pred_t1, label) + 0.5 * criterion(pred_t2, label)
-        loss = 0.5 * loss_s + 0.5 * loss_t
-    else:
-        loss = cfg["SRC_LOSS_WEIGHT"] * loss_s
-    loss_cls = cfg["CLS_WEIGHT"] * loss
     geo, sem = cfg["GEO_MMD"][0], cfg["SEM_MMD"][0]
     # the three MMD terms are independent chains of small kernels (weights, Gram matrix, kernel sums): on three streams
     # when the passes ran concurrently (not with a collective inside mmd_fn: one communicator, one issue order)
@@ -147,6 +141,14 @@ def sug_losses(model, data, label, data_t, label_t, criterion, cfg=SUG_CFG, mmd_
         l1 = sem["SEM_SCALE"] * mmd_fn(label, sem_s1, label_t, sem_t1, sem, data_s=pred_s1, data_t=pred_t1)
     with cp.lane(lanes, 2):
         l2 = sem["SEM_SCALE"] * mmd_fn(label, sem_s2, label_t, sem_t2, sem, data_s=pred_s2, data_t=pred_t2)
+    # the classification losses are issued after the forks, so they run next to the MMD chains
+    loss_s = 0.5 * criterion(pred_s1, label) + 0.5 * criterion(pred_s2, label)
+    if cfg["TARGET_LOSS"] > 0:
+        loss_t = 0.5 * criterion(pred_t1, label) + 0.5 * criterion(pred_t2, label)
+        loss = 0.5 * loss_s + 0.5 * loss_t
+    else:
+        loss = cfg["SRC_LOSS_WEIGHT"] * loss_s
+    loss_cls = cfg["CLS_WEIGHT"] * loss
     cp.merge(lanes, (loss_geo, l1, l2))
     loss_sem = cfg["MMD_WEIGHT"] * (0.5 * l1 + 0.5 * l2)
     cp.join()
