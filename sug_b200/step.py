@@ -26,15 +26,25 @@ _PAIR_STREAMS = {}
 
 
 class ConcurrentPasses:
-    """Runs the two encoder passes of a step (source batch, target batch) CONCURRENTLY on two CUDA streams.
+    """Runs the encoder passes of a step (source / target batch, semantic / node variant) CONCURRENTLY on up to four
+    CUDA streams, then the deferred BatchNorm updates, and offers the same streams as lanes for the loss terms.
 
-    The two passes share nothing but the weights (read-only) and the BatchNorm running buffers; the latter are updated
-    through ``ops.BNRecorder`` AFTER both passes, source first, exactly in the reference's order
+    The passes share nothing but the weights (read-only) and the BatchNorm running buffers; the latter are updated
+    through ``ops.BNRecorder`` AFTER the passes, pass by pass in the reference's order
     (train_dg_single_gpu.py:260-264, 309-310), so losses, gradients and buffers are what the sequential execution
     produces.  What the concurrency buys: the step's kernels come in 3.46 waves of CTAs (64 clouds on 148 SMs) and many
-    of them are latency-bound (FPS, counting sorts, index kernels, small GEMMs): a second stream fills the tails.  The
+    of them are latency-bound (FPS, counting sorts, index kernels, small GEMMs): the other streams fill the tails.  The
     backward follows automatically (autograd runs every node on the stream of its forward).  Captured into the step's
-    CUDA graph as fork / join edges.  Off for CPU tensors, eval mode and the opt-in shared trunk."""
+    CUDA graph as fork / join edges.  Off for CPU tensors, eval mode and the opt-in shared trunk; then ``run`` calls
+    the function in place, ``lanes`` returns None and ``lane`` / ``merge`` / ``join`` do nothing.
+
+        with ConcurrentPasses(model, device) as cp:
+            a = cp.run(0, lambda: model(x)); b = cp.run(1, lambda: model(y))     # concurrent
+        lanes = cp.lanes(2)
+        with cp.lane(lanes, 0): la = loss_a(a)
+        with cp.lane(lanes, 1): lb = loss_b(b)
+        cp.merge(lanes, (la, lb)); cp.join()                                     # current stream owns everything again
+    """
 
     def __init__(self, model, device):
         from . import ops
