@@ -80,3 +80,32 @@ def test_concurrent_passes_are_a_no_op_without_cuda():
         pass
     cp.merge(None, ())
     cp.join()
+
+
+def _bench(args, env_extra, timeout=600):
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SUG_BENCH_CPU_BUDGET_S="1", **env_extra)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), *args], cwd=root, env=env, capture_output=True,
+                       text=True, timeout=timeout)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    return [json.loads(l) for l in lines]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle on the host cores) prints ONE JSON line with the GPU arm's metric,
+    unit and config, `impl: reference`, a cpu_baseline describing itself and a zero-copy e2e; ranks other than 0 of a
+    torchrun launch exit 0 without work and without output.  (The sample is bounded to 4+4 clouds here.)"""
+    out = _bench(["--impl", "reference", "--steps", "1", "--warmup", "0"], {})
+    assert len(out) == 1
+    d = out[0]
+    assert d["impl"] == "reference" and d["metric"] == "DGCNN SUG train clouds/sec" and d["unit"] == "clouds/s"
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0
+    assert d["config"]["workload"] and "model" not in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["execution"]["sample_batch_per_subdomain"] == 4
+    other = _bench(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                   {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert other == []
