@@ -626,7 +626,7 @@ def _main(args, rank, emit):
         except Exception as e:  # never lose the measured line over the comparison arm
             line["torch_gpu_reference"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:  # rank 0 at N = 1 only (the contract); N > 1 lines carry none
         # the reference's CPU path on this box's host cores: BASELINE.json configs[0]-sized sample of the same step
         # (32+32 clouds when the host has the memory), one warm-up step, best of two
         bs = 32 if host_mem_gib() >= 24.0 else (16 if host_mem_gib() >= 14.0 else 8)
